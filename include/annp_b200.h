@@ -1,0 +1,222 @@
+/*
+ * annp_b200.h -- C ABI of libannp_b200.so: the B200 (sm_100a) implementation of the ANNP
+ * neural-network-potential force evaluation behind LAMMPS `pair_style annp/gpu`.
+ *
+ * This is the drop-in boundary.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference repo, annp-gpu-lammps/fe_v2/):
+ *
+ *   annp_b200_init            <- annp_gpu_init      src/pair_annp_gpu.cpp:31-39, lib/lal_annp_ext.cpp:25-92
+ *   annp_b200_neigh           <- ANNP::reset_nbors  lib/lal_annp.cpp:301-304 (ago == 0 branch of compute)
+ *   annp_b200_compute         <- annp_gpu_compute   src/pair_annp_gpu.cpp:51-56, lib/lal_annp_ext.cpp:109-119
+ *   annp_b200_clear           <- annp_gpu_clear     src/pair_annp_gpu.cpp:41,   lib/lal_annp_ext.cpp:94-96
+ *   annp_b200_bytes           <- annp_gpu_bytes     src/pair_annp_gpu.cpp:58,   lib/lal_annp_ext.cpp:121-123
+ *   annp_b200_read_potential  <- PairANNP::read_file src/pair_annp.cpp:332-585 (potential file format)
+ *   annp_b200_neigh_build / annp_b200_compute_device / annp_b200_nve_*  : the device-resident mode
+ *       (replaces the per-step H2D x / D2H f staging of lib/lal_annp.cpp:310-312,336-347 and the
+ *        GPU_NEIGH path annp_gpu_compute_n, lib/lal_annp_ext.cpp:98-108)
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only.  All pointers are caller-owned; init copies what it needs.
+ *   - handle based (the reference keeps one static singleton per process, lal_annp_ext.cpp:20).
+ *   - return value: 0 on success, negative on failure.  -1..-8 keep the meaning of the reference's
+ *     init codes (lib/lal_annp.h:28-33): -3 out of device memory, -4 library built without CUDA
+ *     support / no usable device, -5 device lacks FP64.  Further codes below.  The message of the
+ *     last failure on a handle is available from annp_b200_last_error().
+ *   - there is NO CPU fallback: every compute entry point fails with ANNP_B200_ENODEVICE when no
+ *     sm_100 device is present.
+ *   - not re-entrant per handle; different handles may be used from different threads.
+ */
+#ifndef ANNP_B200_H
+#define ANNP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANNP_B200_ABI_VERSION 1
+
+#define ANNP_B200_MAX_SF 64        /* descriptor components                      */
+#define ANNP_B200_MAX_NOD 32       /* nodes per hidden layer                     */
+#define ANNP_B200_MAX_LAYERS 6     /* weight layers (ntl - 1)                    */
+#define ANNP_B200_MAX_ELEMENTS 4
+#define ANNP_B200_MAX_NEIGH 384    /* in-cutoff neighbours of one atom (smem tile) */
+
+/* error codes */
+#define ANNP_B200_OK 0
+#define ANNP_B200_ENOFIX (-1)      /* kept for parity with the reference's -1    */
+#define ANNP_B200_ENOMEM (-3)
+#define ANNP_B200_ENODEVICE (-4)
+#define ANNP_B200_ENOFP64 (-5)
+#define ANNP_B200_ESPLIT (-8)
+#define ANNP_B200_EINVAL (-20)     /* bad argument / unsupported parameter set   */
+#define ANNP_B200_ECUDA (-21)      /* CUDA runtime error, see last_error         */
+#define ANNP_B200_ESTATE (-22)     /* call order (compute before neigh, ...)     */
+#define ANNP_B200_EOVERFLOW (-23)  /* an atom has more than MAX_NEIGH neighbours inside the cutoff */
+#define ANNP_B200_EIO (-24)        /* potential file unreadable / malformed      */
+
+typedef struct annp_b200_handle_s *annp_b200_handle;
+
+/* descriptor families: flagsym of the reference (src/pair_annp.cpp:415-417) */
+#define ANNP_B200_SYM_CHEBYSHEV 0
+
+/*
+ * Flat parameter block == the argument list of annp_gpu_init (src/pair_annp_gpu.cpp:31-39).
+ *   sfnor_scal[n] = 1/sqrt(cov_n - avg_n^2), 0 if <= 1e-10      (src/pair_annp_gpu.cpp:211-220)
+ *   cutsq  : (ntypes+1) x (ntypes+1), row-major, 1-based types   (host_cutsq)
+ *   map    : ntypes+1 entries, LAMMPS type -> element index      (host_map)
+ *   weights: per element, per layer l = 0..ntl-2, row-major [row * ncol + col] exactly as the
+ *            reference flattens them (src/pair_annp_gpu.cpp:190-209); the blocks of one element are
+ *            concatenated in layer order: nnod*nsf, (ntl-3) x nnod*nnod, nnod; elements follow
+ *            each other.  bias likewise: (ntl-2) x nnod, then 1.
+ */
+typedef struct annp_b200_params {
+  int abi_version;            /* ANNP_B200_ABI_VERSION */
+  int ntypes;
+  int nelements;
+  int ntl, nhl, nnod, nsf, npsf, ntsf;
+  int flagsym;
+  int flagact[ANNP_B200_MAX_LAYERS];
+  double e_scale, e_shift, e_atom;
+  double cut;                 /* descriptor cutoff Rc of the potential file */
+  const double *sfnor_scal;   /* [nsf] */
+  const double *sfnor_avg;    /* [nsf] */
+  const double *cutsq;        /* [(ntypes+1)^2] */
+  const int *map;             /* [ntypes+1] */
+  const double *weights;      /* see above */
+  const double *bias;
+} annp_b200_params;
+
+/* number of doubles in params.weights / params.bias for one element */
+size_t annp_b200_weights_per_element(int ntl, int nnod, int nsf);
+size_t annp_b200_bias_per_element(int ntl, int nnod);
+
+/* ---- potential file (host only, needs no GPU) --------------------------------------------- */
+
+typedef struct annp_b200_potential {
+  int nelements;
+  int ntl, nhl, nnod, nsf, npsf, ntsf;
+  int flagsym;
+  int flagact[ANNP_B200_MAX_LAYERS];
+  double cut, e_scale, e_shift, e_atom;
+  int id_elem[ANNP_B200_MAX_ELEMENTS];
+  double mass[ANNP_B200_MAX_ELEMENTS];
+  char elements[ANNP_B200_MAX_ELEMENTS][16];
+  double sfnor_cov[ANNP_B200_MAX_SF];
+  double sfnor_avg[ANNP_B200_MAX_SF];
+  /* weight_all[elem][layer][row][col] with rows padded to nsf columns, as PairANNP stores it
+   * (src/pair_annp.cpp:441-447); bias_all[elem][layer][node].  malloc'd by the reader. */
+  double *weight_all;   /* [nelements][ntl-1][nnod][nsf] */
+  double *bias_all;     /* [nelements][ntl-1][nnod]      */
+} annp_b200_potential;
+
+/* Parse a `.ann` file the way PairANNP::read_file does (line-index addressing, tab-then-digit-or-
+ * minus tokenisation, CRLF tolerated, "ta"->activation 4 ...).  elements_coeff are the element
+ * names given on the pair_coeff line (used to attach `#<Elem>` weight blocks).  On success the
+ * caller releases the arrays with annp_b200_free_potential. */
+int annp_b200_read_potential(const char *filename, int nelements_coeff, const char *const *elements_coeff,
+                             annp_b200_potential *out, char *err, int errlen);
+void annp_b200_free_potential(annp_b200_potential *pot);
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+
+/* device < 0: use the current CUDA device.  nall_hint/max_nbors_hint size the first allocation
+ * (they are grown on demand, as the reference does in lal_annp.cpp:562-580). */
+int annp_b200_init(const annp_b200_params *params, int device, int nall_hint, int max_nbors_hint,
+                   annp_b200_handle *out, char *err, int errlen);
+void annp_b200_clear(annp_b200_handle h);
+double annp_b200_bytes(annp_b200_handle h);            /* device bytes currently held */
+const char *annp_b200_last_error(annp_b200_handle h);
+
+/* ---- LAMMPS host-list mode (gpu_mode == GPU_FORCE) ------------------------------------------ */
+
+/* Upload a LAMMPS full neighbour list (call when neighbor->ago == 0).  numneigh and firstneigh are
+ * indexed by atom index i = ilist[ii] as in LAMMPS' NeighList; entries are masked with NEIGHMASK. */
+int annp_b200_neigh(annp_b200_handle h, int inum, int nall, const int *ilist, const int *numneigh,
+                    const int *const *firstneigh);
+/* Same list as flat CSR rows in ilist order (offsets has inum+1 entries). */
+int annp_b200_neigh_csr(annp_b200_handle h, int inum, int nall, const int *ilist, const int64_t *offsets,
+                        const int *neigh);
+
+/* One Pair::compute.  x is [nall][3], type [nall] (1-based); outputs may be NULL when not requested.
+ *   f       [nall][3]  ASSIGNED (not accumulated), like the reference (lal_annp.cpp:336-347); ghost
+ *                      rows carry the contributions LAMMPS reverse-communicates to the owners
+ *   eng     sum of atomic energies of the inum centre atoms (eng_vdwl)
+ *   eatom   [inum...]  eatom[ilist[ii]] = E_i      (assigned for centre atoms)
+ *   virial6 per-pair tally sum (xi-xj) (x) (-Fj), LAMMPS order xx,yy,zz,xy,xz,yz; equals
+ *           virial_fdotr_compute over local+ghost
+ *   vatom   [nall][6]  half/half per-atom virial as ev_tally_xyz (assigned) */
+int annp_b200_compute(annp_b200_handle h, int nlocal, int nghost, const double *x, const int *type,
+                      int eflag, int vflag, double *f, double *eng, double *eatom, double *virial6,
+                      double *vatom);
+
+/* ---- device-resident mode ------------------------------------------------------------------- */
+
+/* All pointers below are DEVICE pointers (cudaMalloc'd by the caller, e.g. torch tensors);
+ * stream is a cudaStream_t passed as void* (NULL = default stream).  Nothing is synchronised:
+ * results are valid after the stream reaches this point. */
+
+/* Build the full neighbour list on the device from positions (cell binning).  Atoms 0..nlocal-1 are
+ * centres; partners are all nall atoms within cutneigh.  bbox_lo/hi (host pointers, 3 doubles) bound
+ * all nall positions.  Rows are sorted by neighbour index, so the result is deterministic. */
+int annp_b200_neigh_build(annp_b200_handle h, int nlocal, int nall, const double *d_x, const double *bbox_lo,
+                          const double *bbox_hi, double cutneigh, void *stream);
+
+/* d_f [nall][3] assigned; d_eatom [nlocal] assigned or NULL; d_eng_virial: 7 doubles
+ * (eng, v_xx, v_yy, v_zz, v_xy, v_xz, v_yz) assigned or NULL; d_vatom [nall][6] or NULL. */
+int annp_b200_compute_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, const int *d_type,
+                             int eflag, int vflag, double *d_f, double *d_eatom, double *d_eng_virial,
+                             double *d_vatom, void *stream);
+
+/* Ghosts that are periodic self-images of this rank's own atoms ("communication" inside one rank).
+ * set_ghosts registers owner[g] (local index) and shift[g][3] of ghost g = nlocal + g and builds the
+ * owner-major fold list once (call again after every re-neighbouring).  Device pointers; the arrays
+ * must stay alive until the next set_ghosts.
+ *   update_ghosts: x[nlocal+g] = x[owner[g]] + shift[g]             (forward)
+ *   fold_ghosts  : f[owner[g]] += f[nlocal+g], in ascending g       (reverse, deterministic) */
+int annp_b200_set_ghosts(annp_b200_handle h, int nlocal, int nghost, const int *d_ghost_owner,
+                         const double *d_ghost_shift, void *stream);
+int annp_b200_update_ghosts(annp_b200_handle h, double *d_x, void *stream);
+int annp_b200_fold_ghosts(annp_b200_handle h, double *d_f, void *stream);
+
+/* velocity-Verlet halves for the stand-alone MD loop (metal units; ftm2v = 1/(1.0364269e-4)):
+ *   initial: v += dtf * f / m ; x += dt * v        final: v += dtf * f / m
+ * d_ke (1 double, may be NULL) receives sum 0.5 m v^2 in mass*velocity^2 units on `final`. */
+int annp_b200_nve_initial(annp_b200_handle h, int nlocal, double dt, double mass, double *d_x, double *d_v,
+                          const double *d_f, void *stream);
+int annp_b200_nve_final(annp_b200_handle h, int nlocal, double dt, double mass, double *d_v, const double *d_f,
+                        double *d_ke, void *stream);
+
+/* measured FP64 FMA throughput of this device in TFLOP/s (pure DFMA loop, best of reps): the
+ * denominator of the force kernel's roofline (MEASURED_PEAKS.json has no FP64 entry) */
+double annp_b200_fp64_peak_tflops(annp_b200_handle h, int reps);
+
+/* ---- introspection (tests, bench) ----------------------------------------------------------- */
+
+typedef struct annp_b200_stats {
+  int inum, nall;
+  int max_neigh_list;        /* longest list row                           */
+  int max_neigh_cut;         /* most in-cutoff neighbours of any atom (last compute) */
+  double avg_neigh_cut;      /* mean in-cutoff neighbours (last compute)   */
+  double sum_triplets;       /* sum over atoms of N(N-1)/2 (last compute)  */
+  long long kernel_launches; /* kernels launched by this handle so far     */
+  float last_force_kernel_ms;/* CUDA-event time of the descriptor+force kernel of the last
+                                compute call issued with timing enabled, else 0 */
+} annp_b200_stats;
+int annp_b200_get_stats(annp_b200_handle h, annp_b200_stats *out);   /* synchronises the device */
+int annp_b200_set_timing(annp_b200_handle h, int enabled);
+
+/* centred descriptors G [inum][nsf] and dE/dG [inum][nsf] of the last compute (device->host copy;
+ * test hook replacing the reference's printf debugging). Either pointer may be NULL. */
+int annp_b200_debug_descriptors(annp_b200_handle h, double *G, double *dE_dG);
+
+int annp_b200_abi_version(void);
+/* number of CUDA devices visible to the library (0 = none, no error) */
+int annp_b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANNP_B200_H */

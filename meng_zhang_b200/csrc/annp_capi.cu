@@ -1,0 +1,643 @@
+// annp_capi.cu -- the C ABI of libannp_b200.so (include/annp_b200.h): handle, device buffers and the
+// per-step launch sequence.  No CPU fallback: without an sm_100 device every entry point that needs
+// the GPU returns ANNP_B200_ENODEVICE.
+#include "annp_device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// ---- kernels' host entry points (annp_force.cu / annp_aux.cu / annp_neigh.cu)
+size_t annp_force_smem_bytes(const DevParams &hp, int capacity);
+bool annp_force_supported(int npsf, int ntsf);
+cudaError_t annp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream, int *blocks_out);
+void aux_pack_xq(const double *x, const int *type, double4 *xq, int nall, cudaStream_t s);
+void aux_build_reverse(const int *nbr, long long total, int nall, long long *rev_off, int *rev_pos, int *cnt, int *tmp,
+                       long long *tile_sum, cudaStream_t s);
+void aux_centre_of(const int *ilist, int inum, int nall, int *centre_of, cudaStream_t s);
+void aux_gather_force(const double4 *fpair, const double4 *fself, const int *centre_of, const long long *rev_off,
+                      const int *rev_pos, double *f, int nall, cudaStream_t s);
+void aux_gather_vatom(const double *vpair, const int *centre_of, const long long *row_off, const long long *rev_off,
+                      const int *rev_pos, double *vatom, int nall, cudaStream_t s);
+void aux_scatter_eatom(const double4 *fself, const int *ilist, int inum, double *eatom, cudaStream_t s);
+int aux_reduce_blocks(int inum);
+void aux_reduce_ev(const double4 *fself, const double *vir_c, int inum, double *partial, double *out7, cudaStream_t s);
+void aux_update_ghosts(int nlocal, int nghost, const int *owner, const double *shift, double *x, cudaStream_t s);
+void aux_build_ghost_csr(const int *owner, int nghost, int nlocal, long long *goff, int *glist, int *cnt, int *tmp,
+                         long long *tile_sum, cudaStream_t s);
+void aux_fold_ghosts(int nlocal, const long long *goff, const int *glist, double *f, cudaStream_t s);
+void aux_nve_initial(int n, double dt, double dtfm, double *x, double *v, const double *f, cudaStream_t s);
+void aux_nve_final(int n, double dtfm, double *v, const double *f, cudaStream_t s);
+int aux_ke_blocks(int n);
+void aux_kinetic(int n, const double *v, double half_mass, double *partial, double *out, cudaStream_t s);
+double aux_fp64_peak_tflops(int num_sms, int reps, cudaStream_t s);
+
+struct NeighScratch {
+  int *cell_of, *cell_cnt, *cell_atoms, *row_cnt;
+  long long *cell_off, *tile_sum;
+};
+void neigh_grid(const double *lo, const double *hi, double cutneigh, int *n_out, double *inv_out, long long *ncells);
+void neigh_count(const double *d_x, int nlocal, int nall, const double *lo, const int *n, const double *inv, double cutneigh,
+                 NeighScratch sc, long long *d_row_off, int *d_maxrow, cudaStream_t s);
+void neigh_fill(const double *d_x, int nlocal, const double *lo, const int *n, const double *inv, double cutneigh,
+                NeighScratch sc, const long long *d_row_off, int *d_rows_tmp, int *d_rows, cudaStream_t s);
+
+namespace {
+
+// growable device allocation
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes, double slack = 1.1) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = (size_t) ((double) bytes * slack) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+__global__ void k_count_cut(const DevParams *prm, const double4 *__restrict__ xq, const int *__restrict__ ilist,
+                            const long long *__restrict__ row_off, const int *__restrict__ nbr, int inum, int *__restrict__ maxn) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  const int nt1 = prm->ntypes + 1;
+  int best = 0;
+  for (int ii = wid; ii < inum; ii += nw) {
+    const double4 xi = xq[ilist[ii]];
+    const int ti = (int) xi.w;
+    int n = 0;
+    for (long long p = row_off[ii] + lane; p < row_off[ii + 1]; p += 32) {
+      const double4 xj = xq[nbr[p] & ANNP_NEIGHMASK];
+      const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+      const double rsq = dx * dx + dy * dy + dz * dz;
+      n += !(rsq > prm->cutsq[ti * nt1 + (int) xj.w] || rsq < 1.0e-12);
+    }
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    best = max(best, n);
+  }
+  if (lane == 0) atomicMax(maxn, best);
+}
+
+}    // namespace
+
+struct annp_b200_handle_s {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;      // host-mode stream
+  DevParams hp;                       // host copy (weights/bias pointers are device pointers)
+  DevBuf d_params, d_weights, d_bias;
+  // neighbour list
+  bool have_list = false;
+  int inum = 0, nall_list = 0, max_row = 0;
+  long long total = 0;
+  DevBuf d_ilist, d_row_off, d_nbr, d_rev_off, d_rev_pos, d_centre_of, d_scratch_cnt, d_scratch_tmp, d_tile_sum;
+  // device neighbour build scratch
+  DevBuf d_cell_of, d_cell_cnt, d_cell_off, d_cell_atoms, d_row_cnt, d_small;
+  // per-step
+  DevBuf d_xq, d_fpair, d_fself, d_vir_c, d_vpair, d_partial, d_counters, d_engvir, d_Gdbg, d_dEdbg;
+  // host-mode staging
+  DevBuf d_x, d_type, d_f, d_eatom, d_vatom;
+  // ghosts
+  int g_nlocal = 0, g_nghost = 0;
+  const int *g_owner = nullptr;
+  const double *g_shift = nullptr;
+  DevBuf d_goff, d_glist, d_ke_partial;
+  int capacity = 0;
+  bool need_calibrate = true;
+  bool timing = false;
+  bool debug_desc = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_force_ms = 0.f;
+  bool ev_pending = false;
+  long long launches = 0;
+  DevCounters last_cnt;
+  std::string err;
+};
+
+namespace {
+
+int fail(annp_b200_handle h, int code, const std::string &msg) {
+  if (h) h->err = msg;
+  return code;
+}
+int cuda_fail(annp_b200_handle h, cudaError_t e, const char *where) {
+  return fail(h, e == cudaErrorMemoryAllocation ? ANNP_B200_ENOMEM : ANNP_B200_ECUDA,
+              std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                         \
+  do {                                                                   \
+    cudaError_t e__ = (call);                                            \
+    if (e__ != cudaSuccess) return cuda_fail(h, e__, #call);             \
+  } while (0)
+
+void set_err(char *err, int errlen, const std::string &msg) {
+  if (err && errlen > 0) snprintf(err, (size_t) errlen, "%s", msg.c_str());
+}
+
+int round_capacity(int n) {
+  int c = ((n + 15) / 16) * 16;
+  if (c < 32) c = 32;
+  return c;
+}
+
+int finish_list(annp_b200_handle h, cudaStream_t s) {
+  // reverse map + centre index for the list now in d_ilist / d_row_off / d_nbr
+  const int nall = h->nall_list;
+  if (h->total >= (1LL << 31)) return fail(h, ANNP_B200_EINVAL, "neighbour list has 2^31 or more entries");
+  CK(h->d_rev_off.reserve(sizeof(long long) * ((size_t) nall + 1)));
+  CK(h->d_rev_pos.reserve(sizeof(int) * (size_t) std::max<long long>(h->total, 1)));
+  CK(h->d_scratch_cnt.reserve(sizeof(int) * (size_t) std::max(nall, 1)));
+  CK(h->d_scratch_tmp.reserve(sizeof(int) * (size_t) std::max<long long>(h->total, 1)));
+  CK(h->d_tile_sum.reserve(sizeof(long long) * ((size_t) nall / 1024 + 2)));
+  CK(h->d_centre_of.reserve(sizeof(int) * (size_t) std::max(nall, 1)));
+  aux_build_reverse(h->d_nbr.as<int>(), h->total, nall, h->d_rev_off.as<long long>(), h->d_rev_pos.as<int>(),
+                    h->d_scratch_cnt.as<int>(), h->d_scratch_tmp.as<int>(), h->d_tile_sum.as<long long>(), s);
+  aux_centre_of(h->d_ilist.as<int>(), h->inum, nall, h->d_centre_of.as<int>(), s);
+  h->launches += 9;
+  CK(cudaGetLastError());
+  h->have_list = true;
+  h->need_calibrate = true;
+  return ANNP_B200_OK;
+}
+
+// the per-step device sequence; everything asynchronous on `s`
+int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, const int *d_type, int eflag, int vflag,
+                double *d_f, double *d_eatom, double *d_engvir, double *d_vatom, cudaStream_t s, bool allow_sync) {
+  const int nall = nlocal + nghost;
+  if (!h->have_list) return fail(h, ANNP_B200_ESTATE, "compute called before a neighbour list was provided");
+  if (nall != h->nall_list) return fail(h, ANNP_B200_ESTATE, "nall differs from the neighbour list's nall");
+  const bool want_vir = (vflag != 0) && d_engvir != nullptr;
+  const bool want_vatom = d_vatom != nullptr;
+  const int inum = h->inum;
+
+  CK(h->d_xq.reserve(sizeof(double4) * (size_t) std::max(nall, 1)));
+  CK(h->d_fpair.reserve(sizeof(double4) * (size_t) std::max<long long>(h->total, 1)));
+  CK(h->d_fself.reserve(sizeof(double4) * (size_t) std::max(inum, 1)));
+  CK(h->d_counters.reserve(sizeof(DevCounters)));
+  CK(h->d_partial.reserve(sizeof(double) * 7 * (size_t) aux_reduce_blocks(inum)));
+  if (want_vir || want_vatom) CK(h->d_vir_c.reserve(sizeof(double) * 6 * (size_t) std::max(inum, 1)));
+  if (want_vatom) CK(h->d_vpair.reserve(sizeof(double) * 6 * (size_t) std::max<long long>(h->total, 1)));
+  if (h->debug_desc) {
+    CK(h->d_Gdbg.reserve(sizeof(double) * (size_t) h->hp.nsf * std::max(inum, 1)));
+    CK(h->d_dEdbg.reserve(sizeof(double) * (size_t) h->hp.nsf * std::max(inum, 1)));
+  }
+
+  aux_pack_xq(d_x, d_type, h->d_xq.as<double4>(), nall, s);
+  h->launches += 1;
+
+  if (h->need_calibrate) {
+    // size the shared-memory neighbour tile from the actual in-cutoff maximum (once per list)
+    if (allow_sync) {
+      CK(h->d_small.reserve(64));
+      CK(cudaMemsetAsync(h->d_small.p, 0, sizeof(int), s));
+      if (inum > 0) {
+        k_count_cut<<<std::min(148 * 16, (inum + 7) / 8), 256, 0, s>>>((const DevParams *) h->d_params.p, h->d_xq.as<double4>(), h->d_ilist.as<int>(),
+                                                                     h->d_row_off.as<long long>(), h->d_nbr.as<int>(), inum, h->d_small.as<int>());
+        h->launches += 1;
+      }
+      int maxn = 0;
+      CK(cudaMemcpyAsync(&maxn, h->d_small.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      if (maxn > ANNP_B200_MAX_NEIGH) return fail(h, ANNP_B200_EOVERFLOW, "an atom has more in-cutoff neighbours than ANNP_B200_MAX_NEIGH");
+      h->capacity = std::max(h->capacity, round_capacity(std::min(maxn + 12, ANNP_B200_MAX_NEIGH)));
+    } else {
+      h->capacity = std::max(h->capacity, round_capacity(std::min(h->max_row, ANNP_B200_MAX_NEIGH)));
+    }
+    h->need_calibrate = false;
+    CK(cudaMemsetAsync(h->d_counters.p, 0, sizeof(DevCounters), s));
+  }
+
+  // reset the scheduler and statistics, keep the sticky overflow flag
+  CK(cudaMemsetAsync(h->d_counters.p, 0, offsetof(DevCounters, overflow), s));
+
+  ForceArgs a;
+  a.prm = (const DevParams *) h->d_params.p;
+  a.xq = h->d_xq.as<double4>();
+  a.ilist = h->d_ilist.as<int>();
+  a.row_off = h->d_row_off.as<long long>();
+  a.nbr = h->d_nbr.as<int>();
+  a.fpair = h->d_fpair.as<double4>();
+  a.fself = h->d_fself.as<double4>();
+  a.vir_c = (want_vir || want_vatom) ? h->d_vir_c.as<double>() : nullptr;
+  a.vpair = want_vatom ? h->d_vpair.as<double>() : nullptr;
+  a.G_dbg = h->debug_desc ? h->d_Gdbg.as<double>() : nullptr;
+  a.dEdG_dbg = h->debug_desc ? h->d_dEdbg.as<double>() : nullptr;
+  a.cnt = h->d_counters.as<DevCounters>();
+  a.inum = inum;
+  a.capacity = h->capacity;
+
+  if (inum > 0) {
+    if (h->timing) { CK(cudaEventRecord(h->ev0, s)); }
+    cudaError_t e = annp_force_launch(a, h->hp, h->num_sms, s, nullptr);
+    if (e != cudaSuccess) return cuda_fail(h, e, "annp_force_launch");
+    if (h->timing) { CK(cudaEventRecord(h->ev1, s)); h->ev_pending = true; }
+    h->launches += 1;
+  }
+  if (d_f) {
+    aux_gather_force(h->d_fpair.as<double4>(), h->d_fself.as<double4>(), h->d_centre_of.as<int>(), h->d_rev_off.as<long long>(),
+                     h->d_rev_pos.as<int>(), d_f, nall, s);
+    h->launches += 1;
+  }
+  if (d_engvir && (eflag || vflag)) {
+    aux_reduce_ev(h->d_fself.as<double4>(), want_vir ? h->d_vir_c.as<double>() : nullptr, inum, h->d_partial.as<double>(), d_engvir, s);
+    h->launches += 2;
+  }
+  if (d_eatom) { aux_scatter_eatom(h->d_fself.as<double4>(), h->d_ilist.as<int>(), inum, d_eatom, s); h->launches += 1; }
+  if (want_vatom) {
+    aux_gather_vatom(h->d_vpair.as<double>(), h->d_centre_of.as<int>(), h->d_row_off.as<long long>(), h->d_rev_off.as<long long>(),
+                     h->d_rev_pos.as<int>(), d_vatom, nall, s);
+    h->launches += 1;
+  }
+  CK(cudaGetLastError());
+  return ANNP_B200_OK;
+}
+
+int fetch_counters(annp_b200_handle h, cudaStream_t s) {
+  CK(cudaMemcpyAsync(&h->last_cnt, h->d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (h->ev_pending) {
+    cudaEventSynchronize(h->ev1);
+    cudaEventElapsedTime(&h->last_force_ms, h->ev0, h->ev1);
+    h->ev_pending = false;
+  }
+  return ANNP_B200_OK;
+}
+
+}    // namespace
+
+// ================================================================================================
+extern "C" {
+
+int annp_b200_abi_version(void) { return ANNP_B200_ABI_VERSION; }
+
+int annp_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max_nbors_hint, annp_b200_handle *out,
+                   char *err, int errlen) {
+  (void) nall_hint; (void) max_nbors_hint;
+  if (!p || !out) { set_err(err, errlen, "null argument"); return ANNP_B200_EINVAL; }
+  *out = nullptr;
+  if (p->abi_version != ANNP_B200_ABI_VERSION) { set_err(err, errlen, "ABI version mismatch"); return ANNP_B200_EINVAL; }
+  const int nl = p->ntl - 1;
+  if (p->flagsym != ANNP_B200_SYM_CHEBYSHEV) { set_err(err, errlen, "only the Chebyshev descriptor (flagsym 0) is implemented"); return ANNP_B200_EINVAL; }
+  if (p->ntypes < 1 || p->ntypes > ANNP_MAX_TYPES || p->nelements < 1 || p->nelements > ANNP_B200_MAX_ELEMENTS || nl < 1 ||
+      nl > ANNP_B200_MAX_LAYERS || p->nnod < 1 || p->nnod > ANNP_B200_MAX_NOD || p->nsf != p->npsf + p->ntsf ||
+      p->nsf > ANNP_B200_MAX_SF || p->npsf < 1 || p->ntsf < 1) {
+    set_err(err, errlen, "parameter block outside the supported range");
+    return ANNP_B200_EINVAL;
+  }
+  if (!annp_force_supported(p->npsf, p->ntsf)) {
+    set_err(err, errlen, "no kernel instantiation for this (npsf, ntsf); add it to pick_kernel in annp_force.cu");
+    return ANNP_B200_EINVAL;
+  }
+  if (!p->sfnor_scal || !p->sfnor_avg || !p->cutsq || !p->map || !p->weights || !p->bias) { set_err(err, errlen, "null parameter array"); return ANNP_B200_EINVAL; }
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_err(err, errlen, "no CUDA device: libannp_b200 has no CPU fallback");
+    return ANNP_B200_ENODEVICE;
+  }
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= ndev) { set_err(err, errlen, "device index out of range"); return ANNP_B200_ENODEVICE; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_err(err, errlen, "cannot query device"); return ANNP_B200_ENODEVICE; }
+  if (prop.major < 10) { set_err(err, errlen, "device is not sm_100 class; this library is built for sm_100a only"); return ANNP_B200_ENODEVICE; }
+  if (cudaSetDevice(device) != cudaSuccess) { set_err(err, errlen, "cudaSetDevice failed"); return ANNP_B200_ENODEVICE; }
+
+  annp_b200_handle h = new annp_b200_handle_s();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  DevParams &hp = h->hp;
+  memset(&hp, 0, sizeof(hp));
+  hp.ntypes = p->ntypes; hp.nelements = p->nelements; hp.nlayers = nl; hp.nnod = p->nnod;
+  hp.nsf = p->nsf; hp.npsf = p->npsf; hp.ntsf = p->ntsf;
+  for (int l = 0; l < nl; l++) hp.flagact[l] = p->flagact[l];
+  const int nt1 = p->ntypes + 1;
+  for (int t = 0; t < nt1; t++) hp.map[t] = (t == 0) ? 0 : p->map[t];
+  for (int t = 1; t < nt1; t++)
+    if (hp.map[t] < 0 || hp.map[t] >= p->nelements) { delete h; set_err(err, errlen, "type->element map entry out of range"); return ANNP_B200_EINVAL; }
+  for (int a = 0; a < nt1 * nt1; a++) {
+    hp.cutsq[a] = p->cutsq[a];
+    hp.rcinv[a] = p->cutsq[a] > 0.0 ? 1.0 / sqrt(p->cutsq[a]) : 0.0;
+  }
+  hp.cut = p->cut; hp.two_over_cut = 2.0 / p->cut;
+  hp.e_scale = p->e_scale; hp.e_shift = p->e_shift; hp.e_atom = p->e_atom;
+  for (int n = 0; n < p->nsf; n++) { hp.sf_scale[n] = p->sfnor_scal[n]; hp.sf_avg[n] = p->sfnor_avg[n]; }
+  hp.w_per_elem = (int) annp_b200_weights_per_element(p->ntl, p->nnod, p->nsf);
+  hp.b_per_elem = (int) annp_b200_bias_per_element(p->ntl, p->nnod);
+  {
+    int wo = 0, bo = 0;
+    for (int l = 0; l < nl; l++) {
+      hp.w_off[l] = wo; hp.b_off[l] = bo;
+      const int nr = (l == nl - 1) ? 1 : p->nnod, nc = (l == 0) ? p->nsf : p->nnod;
+      wo += nr * nc; bo += nr;
+    }
+  }
+  auto bail = [&](cudaError_t e, const char *w) {
+    int rc = cuda_fail(h, e, w);
+    set_err(err, errlen, h->err);
+    annp_b200_clear(h);
+    return rc;
+  };
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+  if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  const size_t wbytes = sizeof(double) * (size_t) hp.w_per_elem * p->nelements, bbytes = sizeof(double) * (size_t) hp.b_per_elem * p->nelements;
+  if ((e = h->d_weights.reserve(wbytes, 1.0)) != cudaSuccess) return bail(e, "cudaMalloc weights");
+  if ((e = h->d_bias.reserve(bbytes, 1.0)) != cudaSuccess) return bail(e, "cudaMalloc bias");
+  if ((e = h->d_params.reserve(sizeof(DevParams), 1.0)) != cudaSuccess) return bail(e, "cudaMalloc params");
+  if ((e = cudaMemcpy(h->d_weights.p, p->weights, wbytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload weights");
+  if ((e = cudaMemcpy(h->d_bias.p, p->bias, bbytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload bias");
+  hp.weights = h->d_weights.as<double>();
+  hp.bias = h->d_bias.as<double>();
+  if ((e = cudaMemcpy(h->d_params.p, &hp, sizeof(DevParams), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload params");
+  memset(&h->last_cnt, 0, sizeof(h->last_cnt));
+  *out = h;
+  return ANNP_B200_OK;
+}
+
+void annp_b200_clear(annp_b200_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DevBuf *bufs[] = {&h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
+                    &h->d_centre_of, &h->d_scratch_cnt, &h->d_scratch_tmp, &h->d_tile_sum, &h->d_cell_of, &h->d_cell_cnt,
+                    &h->d_cell_off, &h->d_cell_atoms, &h->d_row_cnt, &h->d_small, &h->d_xq, &h->d_fpair, &h->d_fself, &h->d_vir_c,
+                    &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,
+                    &h->d_eatom, &h->d_vatom, &h->d_goff, &h->d_glist, &h->d_ke_partial};
+  for (DevBuf *b : bufs) b->release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+double annp_b200_bytes(annp_b200_handle h) {
+  if (!h) return 0.0;
+  const DevBuf *bufs[] = {&h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
+                          &h->d_centre_of, &h->d_scratch_cnt, &h->d_scratch_tmp, &h->d_tile_sum, &h->d_cell_of, &h->d_cell_cnt,
+                          &h->d_cell_off, &h->d_cell_atoms, &h->d_row_cnt, &h->d_small, &h->d_xq, &h->d_fpair, &h->d_fself, &h->d_vir_c,
+                          &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,
+                          &h->d_eatom, &h->d_vatom, &h->d_goff, &h->d_glist, &h->d_ke_partial};
+  double b = 0.0;
+  for (const DevBuf *d : bufs) b += (double) d->cap;
+  return b;
+}
+
+const char *annp_b200_last_error(annp_b200_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int annp_b200_neigh_csr(annp_b200_handle h, int inum, int nall, const int *ilist, const int64_t *offsets, const int *neigh) {
+  if (!h) return ANNP_B200_EINVAL;
+  if (inum < 0 || nall < 0 || (inum > 0 && (!ilist || !offsets))) return fail(h, ANNP_B200_EINVAL, "bad neighbour list arguments");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const long long total = inum > 0 ? (long long) offsets[inum] : 0;
+  h->inum = inum; h->nall_list = nall; h->total = total;
+  int maxrow = 0;
+  for (int ii = 0; ii < inum; ii++) maxrow = std::max(maxrow, (int) (offsets[ii + 1] - offsets[ii]));
+  h->max_row = maxrow;
+  CK(h->d_ilist.reserve(sizeof(int) * (size_t) std::max(inum, 1)));
+  CK(h->d_row_off.reserve(sizeof(long long) * ((size_t) inum + 1)));
+  CK(h->d_nbr.reserve(sizeof(int) * (size_t) std::max<long long>(total, 1)));
+  if (inum > 0) {
+    CK(cudaMemcpyAsync(h->d_ilist.p, ilist, sizeof(int) * (size_t) inum, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_row_off.p, offsets, sizeof(long long) * ((size_t) inum + 1), cudaMemcpyHostToDevice, s));
+    if (total > 0) CK(cudaMemcpyAsync(h->d_nbr.p, neigh, sizeof(int) * (size_t) total, cudaMemcpyHostToDevice, s));
+  } else {
+    const long long zero = 0;
+    CK(cudaMemcpyAsync(h->d_row_off.p, &zero, sizeof(long long), cudaMemcpyHostToDevice, s));
+  }
+  int rc = finish_list(h, s);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(s));
+  return ANNP_B200_OK;
+}
+
+int annp_b200_neigh(annp_b200_handle h, int inum, int nall, const int *ilist, const int *numneigh, const int *const *firstneigh) {
+  if (!h) return ANNP_B200_EINVAL;
+  if (inum < 0 || (inum > 0 && (!ilist || !numneigh || !firstneigh))) return fail(h, ANNP_B200_EINVAL, "bad neighbour list arguments");
+  // flatten LAMMPS' paged rows (NeighList::firstneigh) into CSR in ilist order
+  std::vector<int64_t> off((size_t) inum + 1, 0);
+  for (int ii = 0; ii < inum; ii++) off[ii + 1] = off[ii] + numneigh[ilist[ii]];
+  std::vector<int> flat((size_t) off[inum]);
+  for (int ii = 0; ii < inum; ii++) {
+    const int i = ilist[ii];
+    if (numneigh[i] > 0) memcpy(flat.data() + off[ii], firstneigh[i], sizeof(int) * (size_t) numneigh[i]);
+  }
+  return annp_b200_neigh_csr(h, inum, nall, ilist, off.data(), flat.data());
+}
+
+int annp_b200_compute(annp_b200_handle h, int nlocal, int nghost, const double *x, const int *type, int eflag, int vflag,
+                      double *f, double *eng, double *eatom, double *virial6, double *vatom) {
+  if (!h) return ANNP_B200_EINVAL;
+  const int nall = nlocal + nghost;
+  if (nall < 0 || (nall > 0 && (!x || !type))) return fail(h, ANNP_B200_EINVAL, "bad position/type arguments");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  CK(h->d_x.reserve(sizeof(double) * 3 * (size_t) std::max(nall, 1)));
+  CK(h->d_type.reserve(sizeof(int) * (size_t) std::max(nall, 1)));
+  CK(h->d_f.reserve(sizeof(double) * 3 * (size_t) std::max(nall, 1)));
+  CK(h->d_engvir.reserve(sizeof(double) * 8));
+  if (eatom) CK(h->d_eatom.reserve(sizeof(double) * (size_t) std::max(nall, 1)));
+  if (vatom) CK(h->d_vatom.reserve(sizeof(double) * 6 * (size_t) std::max(nall, 1)));
+  if (nall > 0) {
+    CK(cudaMemcpyAsync(h->d_x.p, x, sizeof(double) * 3 * (size_t) nall, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(h->d_type.p, type, sizeof(int) * (size_t) nall, cudaMemcpyHostToDevice, s));
+  }
+  if (eatom) CK(cudaMemsetAsync(h->d_eatom.p, 0, sizeof(double) * (size_t) std::max(nall, 1), s));
+  const bool want_ev = (eng && eflag) || (virial6 && vflag);
+  for (int attempt = 0; attempt < 4; attempt++) {
+    int rc = step_device(h, nlocal, nghost, h->d_x.as<double>(), h->d_type.as<int>(), eflag, (virial6 || vatom) ? (vflag ? vflag : 1) : 0,
+                         f ? h->d_f.as<double>() : nullptr, eatom ? h->d_eatom.as<double>() : nullptr,
+                         want_ev ? h->d_engvir.as<double>() : nullptr, vatom ? h->d_vatom.as<double>() : nullptr, s, true);
+    if (rc) return rc;
+    rc = fetch_counters(h, s);
+    if (rc) return rc;
+    if (!h->last_cnt.overflow) break;
+    // a neighbour tile overflowed (atoms moved inside the skin): grow and redo the step
+    if (h->last_cnt.max_neigh > ANNP_B200_MAX_NEIGH) return fail(h, ANNP_B200_EOVERFLOW, "an atom has more in-cutoff neighbours than ANNP_B200_MAX_NEIGH");
+    h->capacity = round_capacity(std::min(h->last_cnt.max_neigh + 12, ANNP_B200_MAX_NEIGH));
+    CK(cudaMemsetAsync(h->d_counters.p, 0, sizeof(DevCounters), s));
+    if (attempt == 3) return fail(h, ANNP_B200_EOVERFLOW, "neighbour tile kept overflowing");
+  }
+  double ev[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (want_ev) CK(cudaMemcpyAsync(ev, h->d_engvir.p, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
+  if (f && nall > 0) CK(cudaMemcpyAsync(f, h->d_f.p, sizeof(double) * 3 * (size_t) nall, cudaMemcpyDeviceToHost, s));
+  if (eatom && nall > 0) CK(cudaMemcpyAsync(eatom, h->d_eatom.p, sizeof(double) * (size_t) nall, cudaMemcpyDeviceToHost, s));
+  if (vatom && nall > 0) CK(cudaMemcpyAsync(vatom, h->d_vatom.p, sizeof(double) * 6 * (size_t) nall, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (eng && eflag) *eng = ev[0];
+  if (virial6 && vflag) for (int k = 0; k < 6; k++) virial6[k] = ev[1 + k];
+  return ANNP_B200_OK;
+}
+
+int annp_b200_compute_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, const int *d_type, int eflag, int vflag,
+                             double *d_f, double *d_eatom, double *d_eng_virial, double *d_vatom, void *stream) {
+  if (!h) return ANNP_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  return step_device(h, nlocal, nghost, d_x, d_type, eflag, vflag, d_f, d_eatom, d_eng_virial, d_vatom, (cudaStream_t) stream,
+                     /*allow_sync=*/h->need_calibrate);
+}
+
+int annp_b200_neigh_build(annp_b200_handle h, int nlocal, int nall, const double *d_x, const double *bbox_lo, const double *bbox_hi,
+                          double cutneigh, void *stream) {
+  if (!h) return ANNP_B200_EINVAL;
+  if (nlocal < 0 || nall < nlocal || !d_x || !bbox_lo || !bbox_hi || !(cutneigh > 0.0)) return fail(h, ANNP_B200_EINVAL, "bad neigh_build arguments");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t) stream;
+  int n[3];
+  double inv[3];
+  long long ncells = 0;
+  neigh_grid(bbox_lo, bbox_hi, cutneigh, n, inv, &ncells);
+  if (ncells > (1LL << 30)) return fail(h, ANNP_B200_EINVAL, "bounding box too large for the cell grid");
+  CK(h->d_cell_of.reserve(sizeof(int) * (size_t) std::max(nall, 1)));
+  CK(h->d_cell_cnt.reserve(sizeof(int) * (size_t) ncells));
+  CK(h->d_cell_off.reserve(sizeof(long long) * ((size_t) ncells + 1)));
+  CK(h->d_cell_atoms.reserve(sizeof(int) * (size_t) std::max(nall, 1)));
+  CK(h->d_row_cnt.reserve(sizeof(int) * (size_t) std::max(nlocal, 1)));
+  CK(h->d_tile_sum.reserve(sizeof(long long) * ((size_t) std::max<long long>(std::max<long long>(ncells, nall), 1) / 1024 + 2)));
+  CK(h->d_row_off.reserve(sizeof(long long) * ((size_t) nlocal + 1)));
+  CK(h->d_ilist.reserve(sizeof(int) * (size_t) std::max(nlocal, 1)));
+  CK(h->d_small.reserve(64));
+  NeighScratch sc;
+  sc.cell_of = h->d_cell_of.as<int>(); sc.cell_cnt = h->d_cell_cnt.as<int>(); sc.cell_atoms = h->d_cell_atoms.as<int>();
+  sc.row_cnt = h->d_row_cnt.as<int>(); sc.cell_off = h->d_cell_off.as<long long>(); sc.tile_sum = h->d_tile_sum.as<long long>();
+  neigh_count(d_x, nlocal, nall, bbox_lo, n, inv, cutneigh, sc, h->d_row_off.as<long long>(), h->d_small.as<int>(), s);
+  h->launches += 12;
+  long long total = 0;
+  int maxrow = 0;
+  CK(cudaMemcpyAsync(&total, h->d_row_off.as<long long>() + nlocal, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&maxrow, h->d_small.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  h->inum = nlocal; h->nall_list = nall; h->total = total; h->max_row = maxrow;
+  CK(h->d_nbr.reserve(sizeof(int) * (size_t) std::max<long long>(total, 1)));
+  CK(h->d_scratch_tmp.reserve(sizeof(int) * (size_t) std::max<long long>(total, 1)));
+  neigh_fill(d_x, nlocal, bbox_lo, n, inv, cutneigh, sc, h->d_row_off.as<long long>(), h->d_scratch_tmp.as<int>(), h->d_nbr.as<int>(), s);
+  h->launches += 2;
+  // ilist = 0..nlocal-1
+  {
+    std::vector<int> il((size_t) nlocal);
+    for (int i = 0; i < nlocal; i++) il[i] = i;
+    if (nlocal > 0) CK(cudaMemcpyAsync(h->d_ilist.p, il.data(), sizeof(int) * (size_t) nlocal, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return finish_list(h, s);
+}
+
+int annp_b200_set_ghosts(annp_b200_handle h, int nlocal, int nghost, const int *d_owner, const double *d_shift, void *stream) {
+  if (!h) return ANNP_B200_EINVAL;
+  if (nlocal < 0 || nghost < 0 || (nghost > 0 && (!d_owner || !d_shift))) return fail(h, ANNP_B200_EINVAL, "bad ghost arguments");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t) stream;
+  h->g_nlocal = nlocal; h->g_nghost = nghost; h->g_owner = d_owner; h->g_shift = d_shift;
+  CK(h->d_goff.reserve(sizeof(long long) * ((size_t) nlocal + 1)));
+  CK(h->d_glist.reserve(sizeof(int) * (size_t) std::max(nghost, 1)));
+  CK(h->d_scratch_cnt.reserve(sizeof(int) * (size_t) std::max(nlocal, 1)));
+  CK(h->d_scratch_tmp.reserve(sizeof(int) * (size_t) std::max(nghost, 1)));
+  CK(h->d_tile_sum.reserve(sizeof(long long) * ((size_t) nlocal / 1024 + 2)));
+  aux_build_ghost_csr(d_owner, nghost, nlocal, h->d_goff.as<long long>(), h->d_glist.as<int>(), h->d_scratch_cnt.as<int>(),
+                      h->d_scratch_tmp.as<int>(), h->d_tile_sum.as<long long>(), s);
+  h->launches += 7;
+  CK(cudaGetLastError());
+  return ANNP_B200_OK;
+}
+
+int annp_b200_update_ghosts(annp_b200_handle h, double *d_x, void *stream) {
+  if (!h || !d_x) return ANNP_B200_EINVAL;
+  aux_update_ghosts(h->g_nlocal, h->g_nghost, h->g_owner, h->g_shift, d_x, (cudaStream_t) stream);
+  h->launches += 1;
+  return ANNP_B200_OK;
+}
+
+int annp_b200_fold_ghosts(annp_b200_handle h, double *d_f, void *stream) {
+  if (!h || !d_f) return ANNP_B200_EINVAL;
+  aux_fold_ghosts(h->g_nlocal, h->d_goff.as<long long>(), h->d_glist.as<int>(), d_f, (cudaStream_t) stream);
+  h->launches += 1;
+  return ANNP_B200_OK;
+}
+
+// LAMMPS metal units: ftm2v = 1 / 1.0364269e-4, mvv2e = 1.0364269e-4   (update.cpp, units metal)
+static const double kFtm2v = 1.0 / 1.0364269e-4;
+static const double kMvv2e = 1.0364269e-4;
+
+int annp_b200_nve_initial(annp_b200_handle h, int nlocal, double dt, double mass, double *d_x, double *d_v, const double *d_f, void *stream) {
+  if (!h || !d_x || !d_v || !d_f || !(mass > 0.0)) return ANNP_B200_EINVAL;
+  aux_nve_initial(nlocal, dt, 0.5 * dt * kFtm2v / mass, d_x, d_v, d_f, (cudaStream_t) stream);
+  h->launches += 1;
+  return ANNP_B200_OK;
+}
+
+int annp_b200_nve_final(annp_b200_handle h, int nlocal, double dt, double mass, double *d_v, const double *d_f, double *d_ke, void *stream) {
+  if (!h || !d_v || !d_f || !(mass > 0.0)) return ANNP_B200_EINVAL;
+  aux_nve_final(nlocal, 0.5 * dt * kFtm2v / mass, d_v, d_f, (cudaStream_t) stream);
+  h->launches += 1;
+  if (d_ke) {
+    CK(h->d_ke_partial.reserve(sizeof(double) * (size_t) aux_ke_blocks(nlocal)));
+    aux_kinetic(nlocal, d_v, 0.5 * mass * kMvv2e, h->d_ke_partial.as<double>(), d_ke, (cudaStream_t) stream);
+    h->launches += 2;
+  }
+  return ANNP_B200_OK;
+}
+
+double annp_b200_fp64_peak_tflops(annp_b200_handle h, int reps) {
+  if (!h) return -1.0;
+  cudaSetDevice(h->device);
+  return aux_fp64_peak_tflops(h->num_sms, reps < 1 ? 1 : reps, h->stream);
+}
+
+int annp_b200_get_stats(annp_b200_handle h, annp_b200_stats *out) {
+  if (!h || !out) return ANNP_B200_EINVAL;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  if (h->d_counters.p) {
+    int rc = fetch_counters(h, h->stream);
+    if (rc) return rc;
+  }
+  out->inum = h->inum; out->nall = h->nall_list; out->max_neigh_list = h->max_row;
+  out->max_neigh_cut = h->last_cnt.max_neigh;
+  out->avg_neigh_cut = h->inum > 0 ? (double) h->last_cnt.sum_neigh / h->inum : 0.0;
+  out->sum_triplets = (double) h->last_cnt.sum_trip;
+  out->kernel_launches = h->launches;
+  out->last_force_kernel_ms = h->last_force_ms;
+  if (h->last_cnt.overflow) return fail(h, ANNP_B200_EOVERFLOW, "neighbour tile overflow in a device-mode step: results of that step are invalid");
+  return ANNP_B200_OK;
+}
+
+int annp_b200_set_timing(annp_b200_handle h, int enabled) {
+  if (!h) return ANNP_B200_EINVAL;
+  h->timing = enabled != 0;
+  return ANNP_B200_OK;
+}
+
+int annp_b200_debug_descriptors(annp_b200_handle h, double *G, double *dE_dG) {
+  if (!h) return ANNP_B200_EINVAL;
+  if (!h->debug_desc) { h->debug_desc = true; return ANNP_B200_OK; }   // first call arms the capture
+  if (!h->d_Gdbg.p) return fail(h, ANNP_B200_ESTATE, "no compute since the capture was armed");
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  const size_t n = sizeof(double) * (size_t) h->hp.nsf * h->inum;
+  if (G) CK(cudaMemcpy(G, h->d_Gdbg.p, n, cudaMemcpyDeviceToHost));
+  if (dE_dG) CK(cudaMemcpy(dE_dG, h->d_dEdbg.p, n, cudaMemcpyDeviceToHost));
+  return ANNP_B200_OK;
+}
+
+}    // extern "C"

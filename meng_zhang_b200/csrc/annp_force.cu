@@ -1,0 +1,481 @@
+// annp_force.cu -- the fused ANNP force kernel for sm_100a.
+//
+// One warp owns one centre atom at a time (dynamic atom scheduler).  For that atom it
+//   1. filters the LAMMPS list row to the in-cutoff neighbours (ballot compaction keeps list order),
+//      caches unit vector / fc / dfc / r per neighbour in shared memory and accumulates the radial
+//      Chebyshev sums                                   (reference: pair_annp.cpp:134-153, 633-656)
+//   2. walks every unordered neighbour pair (j,k) ONCE with a circulant schedule (lane <-> j,
+//      step <-> offset d, k = (j+d) mod N) and accumulates the 19 angular sums in registers
+//                                                       (reference: pair_annp.cpp:156-176, 658-695)
+//   3. runs the element's MLP forward and reverse-mode backprop -> E_i and dE/dG
+//                                                       (reference: pair_annp.cpp:741-804)
+//   4. walks the pairs a second time, evaluating  A(y) = sum_n c_n T_n(y) and A'(y)  in the Chebyshev
+//      U basis (3 FMA per order) and accumulating, per neighbour, the five moments
+//          V = sum_k P u_k,  S = sum_k P cos(theta),  Aa = sum_k A fc_k     (P = A'/2 fc_j fc_k)
+//      j side in registers, k side by conflict-free shared-memory read-modify-write (all lanes of a
+//      step hit distinct k), so dG/dx is never materialised and no floating-point atomics are used
+//   5. turns the moments into the force on every neighbour, F_j = -e_scale dOut/dx_j
+//      (reference: pair_annp.cpp:191-200), writes it at the neighbour's LIST position (a later
+//      gather kernel sums them per atom in a fixed order), and reduces F_i = -sum F_j, the
+//      per-centre virial and the energy.
+//
+// All arithmetic is IEEE FP64 (the reference CPU pair style is the parity target); the kernel is bound
+// by the FP64 FMA pipe, see DESIGN.md.
+#include "annp_device.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;            // warps per block; each warp is independent
+constexpr double kPi = 3.14159265358979323846;
+
+struct PassDesc {
+  int j, dlo, dhi, nsteps, group, splits;
+  bool active;
+};
+
+// Work split of chunk c (32 lanes) of the N neighbour rows. Full chunks: lane <-> row, offsets 1..D.
+// The ragged tail chunk (R < 32 rows) splits the offset range over 2 or 4 lane groups so that all
+// lanes stay busy; groups are H >= R offsets apart, hence still hit distinct k in every step.
+__device__ __forceinline__ PassDesc make_pass(int c, int N, int D, int lane) {
+  PassDesc p;
+  const int base = c * 32;
+  const int R = N - base;
+  if (R >= 32) {
+    p.j = base + lane; p.dlo = 1; p.dhi = D; p.nsteps = D; p.group = 0; p.splits = 1; p.active = true;
+    return p;
+  }
+  int splits = 1;
+  if (N >= 64) splits = (R <= 8) ? 4 : ((R <= 16) ? 2 : 1);
+  const int rpad = 32 / splits;
+  const int g = lane / rpad, jr = lane - g * rpad;
+  const int H = (D + splits - 1) / splits;
+  p.active = jr < R;
+  p.j = base + jr;
+  p.dlo = 1 + g * H;
+  p.dhi = min(D, p.dlo + H - 1);
+  p.nsteps = H;
+  p.group = g;
+  p.splits = splits;
+  return p;
+}
+
+__device__ __forceinline__ void activation(int flag, double z, double &h, double &hd) {
+  // reference table: pair_annp.cpp:709-739 (Fe copy)
+  const double ca = 1.7159, cb = 0.666666666666667, cc = 0.1;
+  double t;
+  switch (flag) {
+    case 0: h = z; hd = 1.0; break;
+    case 1: h = tanh(z); hd = 1.0 - h * h; break;
+    case 2: h = 1.0 / (1.0 + exp(z)); hd = h * (1.0 - h); break;
+    case 3: t = tanh(cb * z); h = ca * t; hd = ca * (1.0 - t * t) * cb; break;
+    default: t = tanh(cb * z); h = ca * t + cc * z; hd = ca * (1.0 - t * t) * cb + cc; break;
+  }
+}
+
+template <int NPSF, int NTSF>
+__global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const DevParams &P = *a.prm;
+  const int C = a.capacity;
+  const int nsf = NPSF + NTSF, nnod = P.nnod, nl = P.nlayers, nt1 = P.ntypes + 1;
+  const int wtot = P.nelements * P.w_per_elem, btot = P.nelements * P.b_per_elem;
+
+  // ---- block-shared parameters
+  double *sW = reinterpret_cast<double *>(smem_raw);
+  double *sBias = sW + wtot;
+  double *sScale = sBias + btot;
+  double *sAvg = sScale + nsf;
+  double *blk_end = sAvg + nsf;
+  for (int t = threadIdx.x; t < wtot; t += blockDim.x) sW[t] = P.weights[t];
+  for (int t = threadIdx.x; t < btot; t += blockDim.x) sBias[t] = P.bias[t];
+  for (int t = threadIdx.x; t < nsf; t += blockDim.x) { sScale[t] = P.sf_scale[t]; sAvg[t] = P.sf_avg[t]; }
+
+  // ---- per-warp region
+  const size_t per_warp_doubles = (size_t) 11 * C + 2 * NTSF + 2 * NPSF + 2 * nsf + (size_t) 2 * nl * nnod + 2 * nnod;
+  size_t warp_bytes = per_warp_doubles * sizeof(double) + (size_t) C * sizeof(int);
+  warp_bytes = (warp_bytes + 15) & ~(size_t) 15;
+  size_t blk_bytes = ((size_t) ((unsigned char *) blk_end - smem_raw) + 15) & ~(size_t) 15;
+  unsigned char *wbase = smem_raw + blk_bytes + (size_t) warp * warp_bytes;
+  double2 *sA = reinterpret_cast<double2 *>(wbase);   // ux, uy
+  double2 *sB = sA + C;                               // uz, fc
+  double2 *sC = sB + C;                               // dfc, r
+  double2 *accA = sC + C;                             // Vx, Vy
+  double2 *accB = accA + C;                           // Vz, S
+  double *accC = reinterpret_cast<double *>(accB + C);   // Aa
+  double2 *coefT = reinterpret_cast<double2 *>(accC + C);   // angular (d_n, e_n) in the U basis
+  double2 *coefR = coefT + NTSF;                      // radial  (d_m, e_m)
+  double *sG = reinterpret_cast<double *>(coefR + NPSF);
+  double *sdE = sG + nsf;
+  double *sH = sdE + nsf;                             // [nl][nnod] activations
+  double *sHd = sH + nl * nnod;                       // [nl][nnod] activation derivatives
+  double *sDel = sHd + nl * nnod;                     // [2][nnod] backprop deltas
+  int *spos = reinterpret_cast<int *>(sDel + 2 * nnod);
+  __syncthreads();
+
+  const double two_over_cut = P.two_over_cut;
+
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(&a.cnt->work, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= (unsigned long long) a.inum) break;
+    const int ii = (int) item;
+    const int i = a.ilist[ii];
+    const double4 xi = a.xq[i];
+    const int ti = (int) xi.w;
+    const long long p0 = a.row_off[ii];
+    const int L = (int) (a.row_off[ii + 1] - p0);
+
+    // ------------------------------------------------------------------ 1. filter + radial sums
+    double gr[NPSF];
+#pragma unroll
+    for (int m = 0; m < NPSF; m++) gr[m] = 0.0;
+    int N = 0;
+    for (int base = 0; base < L; base += 32) {
+      const int q = base + lane;
+      const bool valid = q < L;
+      bool in = false;
+      double dx = 0, dy = 0, dz = 0, rsq = 0, rci = 0;
+      if (valid) {
+        const int j = a.nbr[p0 + q] & ANNP_NEIGHMASK;
+        const double4 xj = a.xq[j];
+        dx = xi.x - xj.x; dy = xi.y - xj.y; dz = xi.z - xj.z;
+        rsq = dx * dx + dy * dy + dz * dz;
+        const int tj = (int) xj.w;
+        const double csq = P.cutsq[ti * nt1 + tj];
+        rci = P.rcinv[ti * nt1 + tj];
+        in = !(rsq > csq || rsq < 1.0e-12);          // pair_annp.cpp:144
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, in);
+      const int slot = N + __popc(mask & ((1u << lane) - 1u));
+      if (in && slot < C) {
+        const double r = sqrt(rsq);
+        const double rinv = 1.0 / r;
+        double sn, cs;
+        sincospi(r * rci, &sn, &cs);
+        const double fc = 0.5 * (cs + 1.0);          // pair_annp.cpp:590-594
+        const double dfc = -0.5 * kPi * rci * sn;
+        sA[slot] = make_double2(dx * rinv, dy * rinv);
+        sB[slot] = make_double2(dz * rinv, fc);
+        sC[slot] = make_double2(dfc, r);
+        accA[slot] = make_double2(0.0, 0.0);
+        accB[slot] = make_double2(0.0, 0.0);
+        accC[slot] = 0.0;
+        spos[slot] = q;
+        // radial Chebyshev sums, argument 2r/Rc - 1    (pair_annp.cpp:643-647)
+        const double xr = r * two_over_cut - 1.0, xr2 = xr + xr;
+        double t0 = 1.0, t1 = xr;
+        gr[0] += fc;
+        if (NPSF > 1) gr[1] = fma(t1, fc, gr[1]);
+#pragma unroll
+        for (int m = 2; m < NPSF; m++) {
+          const double t = fma(xr2, t1, -t0);
+          gr[m] = fma(t, fc, gr[m]);
+          t0 = t1; t1 = t;
+        }
+      } else if (valid) {
+        a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (a.vpair) {
+          double *vp = a.vpair + (size_t) (p0 + q) * 6;
+#pragma unroll
+          for (int k = 0; k < 6; k++) vp[k] = 0.0;
+        }
+      }
+      N += __popc(mask);
+    }
+    if (lane == 0) {
+      atomicMax(&a.cnt->max_neigh, N);
+      atomicAdd(&a.cnt->sum_neigh, (unsigned long long) N);
+      atomicAdd(&a.cnt->sum_trip, (unsigned long long) N * (unsigned long long) (N > 0 ? N - 1 : 0) / 2ull);
+    }
+    if (N > C) {   // capacity exceeded: flag it, emit zeros; the host re-runs with a larger tile
+      if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
+      for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+      __syncwarp();
+      continue;
+    }
+    __syncwarp();
+
+    const int D = N >> 1;
+    const bool n_even = (N & 1) == 0;
+    const int nchunks = (N + 31) >> 5;
+
+    // ------------------------------------------------------------------ 2. angular sums (forward)
+    double S[NTSF];
+#pragma unroll
+    for (int n = 0; n < NTSF; n++) S[n] = 0.0;
+    for (int c = 0; c < nchunks; c++) {
+      const PassDesc ps = make_pass(c, N, D, lane);
+      double ujx = 0, ujy = 0, ujz = 0, fcj = 0;
+      if (ps.active) {
+        const double2 A = sA[ps.j], B = sB[ps.j];
+        ujx = A.x; ujy = A.y; ujz = B.x; fcj = B.y;
+      }
+      for (int t = 0; t < ps.nsteps; t++) {
+        const int d = ps.dlo + t;
+        const bool ok = ps.active && d <= ps.dhi && !(n_even && d == D && ps.j >= D);
+        if (ok) {
+          int k = ps.j + d;
+          if (k >= N) k -= N;
+          const double2 A = sA[k], B = sB[k];
+          const double y2 = fma(ujx, A.x, fma(ujy, A.y, fma(ujz, B.x, 1.0)));   // cos(theta) + 1
+          const double w = fcj * B.y;
+          const double y = 0.5 * y2;                                            // pair_annp.cpp:671
+          S[0] += w;
+          if (NTSF > 1) S[1] = fma(w, y, S[1]);
+          double t0 = 1.0, t1 = y;
+#pragma unroll
+          for (int n = 2; n < NTSF; n++) {
+            const double tn = fma(y2, t1, -t0);
+            S[n] = fma(w, tn, S[n]);
+            t0 = t1; t1 = tn;
+          }
+        }
+      }
+    }
+    // warp reduction (fixed butterfly order -> deterministic), scaling and centring (pair_annp.cpp:178-180)
+#pragma unroll
+    for (int m = 0; m < NPSF; m++) {
+      const double v = warp_sum(gr[m]);
+      if (lane == 0) sG[m] = sScale[m] * v - sScale[m] * sAvg[m];
+    }
+#pragma unroll
+    for (int n = 0; n < NTSF; n++) {
+      const double v = warp_sum(S[n]);
+      if (lane == 0) sG[NPSF + n] = sScale[NPSF + n] * v - sScale[NPSF + n] * sAvg[NPSF + n];
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ 3. MLP forward + backprop
+    const int elem = P.map[ti];
+    const double *We = sW + elem * P.w_per_elem;
+    const double *Be = sBias + elem * P.b_per_elem;
+    {
+      const double *in = sG;
+      for (int l = 0; l < nl; l++) {
+        const int nr = (l == nl - 1) ? 1 : nnod;
+        const int nc = (l == 0) ? nsf : nnod;
+        const double *W = We + P.w_off[l];
+        if (lane < nr) {
+          double z = 0.0;
+          for (int cidx = 0; cidx < nc; cidx++) z = fma(W[lane * nc + cidx], in[cidx], z);
+          z += Be[P.b_off[l] + lane];
+          double h, hd;
+          activation(P.flagact[l], z, h, hd);
+          sH[l * nnod + lane] = h;
+          sHd[l * nnod + lane] = hd;
+        }
+        __syncwarp();
+        in = sH + l * nnod;
+      }
+    }
+    const double out = sH[(nl - 1) * nnod];
+    const double e_i = P.e_scale * out + P.e_shift + P.e_atom;      // pair_annp.cpp:790-793
+    {
+      // delta_l[r] = d out / d z_l[r]
+      double *dcur = sDel, *dprev = sDel + nnod;
+      if (lane == 0) dcur[0] = sHd[(nl - 1) * nnod];
+      __syncwarp();
+      for (int l = nl - 1; l >= 1; l--) {
+        const int nr = (l == nl - 1) ? 1 : nnod;
+        const double *W = We + P.w_off[l];           // [nr][nnod]
+        if (lane < nnod) {
+          double s = 0.0;
+          for (int r = 0; r < nr; r++) s = fma(W[r * nnod + lane], dcur[r], s);
+          dprev[lane] = s * sHd[(l - 1) * nnod + lane];
+        }
+        __syncwarp();
+        double *tmp = dcur; dcur = dprev; dprev = tmp;
+      }
+      const int nr0 = (nl == 1) ? 1 : nnod;
+      const double *W0 = We + P.w_off[0];            // [nr0][nsf]
+      for (int n = lane; n < nsf; n += 32) {
+        double s = 0.0;
+        for (int r = 0; r < nr0; r++) s = fma(W0[r * nsf + n], dcur[r], s);
+        sdE[n] = s;
+      }
+      __syncwarp();
+    }
+    if (a.G_dbg) for (int n = lane; n < nsf; n += 32) { a.G_dbg[(size_t) ii * nsf + n] = sG[n]; a.dEdG_dbg[(size_t) ii * nsf + n] = sdE[n]; }
+
+    // Chebyshev-T coefficients c_n = s_n dOut/dG_n  ->  U-basis coefficients
+    //   sum c_n T_n = sum d_n U_n,  d_0 = c_0 - c_2/2, d_n = (c_n - c_{n+2})/2
+    //   d/dy sum c_n T_n = sum_{m} (m+1) c_{m+1} U_m        (angular e_m carries the reference's 1/2)
+    if (lane < NTSF) {
+      const int n = lane;
+      const double c0 = sdE[NPSF + n] * sScale[NPSF + n];
+      const double c1 = (n + 1 < NTSF) ? sdE[NPSF + n + 1] * sScale[NPSF + n + 1] : 0.0;
+      const double c2 = (n + 2 < NTSF) ? sdE[NPSF + n + 2] * sScale[NPSF + n + 2] : 0.0;
+      const double dn = (n == 0) ? (c0 - 0.5 * c2) : 0.5 * (c0 - c2);
+      coefT[n] = make_double2(dn, 0.5 * (double) (n + 1) * c1);
+    }
+    if (lane < NPSF) {
+      const int n = lane;
+      const double c0 = sdE[n] * sScale[n];
+      const double c1 = (n + 1 < NPSF) ? sdE[n + 1] * sScale[n + 1] : 0.0;
+      const double c2 = (n + 2 < NPSF) ? sdE[n + 2] * sScale[n + 2] : 0.0;
+      const double dn = (n == 0) ? (c0 - 0.5 * c2) : 0.5 * (c0 - c2);
+      coefR[n] = make_double2(dn, (double) (n + 1) * c1);
+    }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ 4. angular moments (backward)
+    for (int c = 0; c < nchunks; c++) {
+      const PassDesc ps = make_pass(c, N, D, lane);
+      double ujx = 0, ujy = 0, ujz = 0, fcj = 0;
+      if (ps.active) {
+        const double2 A = sA[ps.j], B = sB[ps.j];
+        ujx = A.x; ujy = A.y; ujz = B.x; fcj = B.y;
+      }
+      double vx = 0, vy = 0, vz = 0, ss = 0, aa = 0;
+      for (int t = 0; t < ps.nsteps; t++) {
+        const int d = ps.dlo + t;
+        const bool ok = ps.active && d <= ps.dhi && !(n_even && d == D && ps.j >= D);
+        if (ok) {
+          int k = ps.j + d;
+          if (k >= N) k -= N;
+          const double2 A = sA[k], B = sB[k];
+          const double ct = fma(ujx, A.x, fma(ujy, A.y, ujz * B.x));
+          const double y2 = ct + 1.0;                  // U_1(y) = 2y = cos(theta) + 1
+          double u0 = 1.0, u1 = y2;
+          const double2 q0 = coefT[0];
+          double Ay = q0.x, Apy = q0.y;
+          if (NTSF > 1) { const double2 q1 = coefT[1]; Ay = fma(q1.x, u1, Ay); Apy = fma(q1.y, u1, Apy); }
+#pragma unroll
+          for (int n = 2; n < NTSF; n++) {
+            const double un = fma(y2, u1, -u0);
+            const double2 qn = coefT[n];
+            Ay = fma(qn.x, un, Ay);
+            if (n < NTSF - 1) Apy = fma(qn.y, un, Apy);
+            u0 = u1; u1 = un;
+          }
+          const double Pw = Apy * (fcj * B.y);
+          // j side (registers)
+          vx = fma(Pw, A.x, vx); vy = fma(Pw, A.y, vy); vz = fma(Pw, B.x, vz);
+          ss = fma(Pw, ct, ss);
+          aa = fma(Ay, B.y, aa);
+          // k side (shared memory, distinct k per lane in this step)
+          double2 ka = accA[k], kb = accB[k];
+          double kc = accC[k];
+          ka.x = fma(Pw, ujx, ka.x); ka.y = fma(Pw, ujy, ka.y);
+          kb.x = fma(Pw, ujz, kb.x); kb.y = fma(Pw, ct, kb.y);
+          kc = fma(Ay, fcj, kc);
+          accA[k] = ka; accB[k] = kb; accC[k] = kc;
+        }
+        __syncwarp();
+      }
+      // flush the j side; lane groups of a split tail chunk share rows -> one group at a time
+      for (int g = 0; g < ps.splits; g++) {
+        if (ps.active && ps.group == g) {
+          double2 ja = accA[ps.j], jb = accB[ps.j];
+          ja.x += vx; ja.y += vy; jb.x += vz; jb.y += ss;
+          accA[ps.j] = ja; accB[ps.j] = jb;
+          accC[ps.j] += aa;
+        }
+        __syncwarp();
+      }
+    }
+
+    // ------------------------------------------------------------------ 5. forces on the neighbours
+    double fix = 0, fiy = 0, fiz = 0;
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
+    const double mes = -P.e_scale;
+    for (int s = lane; s < N; s += 32) {
+      const double2 A = sA[s], B = sB[s], Cc = sC[s];
+      const double2 va = accA[s], vb = accB[s];
+      const double aa = accC[s];
+      const double ux = A.x, uy = A.y, uz = B.x, fc = B.y, dfc = Cc.x, r = Cc.y;
+      const double rinv = 1.0 / r;
+      // radial polynomial R(x) = sum c_m T_m(x) and R'(x) in the U basis
+      const double x2 = 2.0 * (r * two_over_cut - 1.0);
+      double u0 = 1.0, u1 = x2;
+      const double2 q0 = coefR[0];
+      double Rv = q0.x, Rp = q0.y;
+      if (NPSF > 1) { const double2 q1 = coefR[1]; Rv = fma(q1.x, u1, Rv); Rp = fma(q1.y, u1, Rp); }
+#pragma unroll
+      for (int m = 2; m < NPSF; m++) {
+        const double un = fma(x2, u1, -u0);
+        const double2 qm = coefR[m];
+        Rv = fma(qm.x, un, Rv);
+        if (m < NPSF - 1) Rp = fma(qm.y, un, Rp);
+        u0 = u1; u1 = un;
+      }
+      // d out / d x_j = g u_j - V / r       with dr/dx_j = -u_j, dcos/dx_j = (cos u_j - u_k)/r
+      const double g = -(Rp * two_over_cut * fc + Rv * dfc) - dfc * aa + vb.y * rinv;
+      const double gx = g * ux - va.x * rinv;
+      const double gy = g * uy - va.y * rinv;
+      const double gz = g * uz - vb.x * rinv;
+      const double Fx = mes * gx, Fy = mes * gy, Fz = mes * gz;     // pair_annp.cpp:197
+      const int q = spos[s];
+      a.fpair[p0 + q] = make_double4(Fx, Fy, Fz, 0.0);
+      fix -= Fx; fiy -= Fy; fiz -= Fz;
+      if (a.vir_c || a.vpair) {
+        // ev_tally_xyz(i, j, ..., -Fj, xi - xj)     (pair_annp.cpp:201-209)
+        const double delx = r * ux, dely = r * uy, delz = r * uz;
+        const double w0 = -delx * Fx, w1 = -dely * Fy, w2 = -delz * Fz;
+        const double w3 = -delx * Fy, w4 = -delx * Fz, w5 = -dely * Fz;
+        v0 += w0; v1 += w1; v2 += w2; v3 += w3; v4 += w4; v5 += w5;
+        if (a.vpair) {
+          double *vp = a.vpair + (size_t) (p0 + q) * 6;
+          vp[0] = w0; vp[1] = w1; vp[2] = w2; vp[3] = w3; vp[4] = w4; vp[5] = w5;
+        }
+      }
+    }
+    fix = warp_sum(fix); fiy = warp_sum(fiy); fiz = warp_sum(fiz);
+    if (lane == 0) a.fself[ii] = make_double4(fix, fiy, fiz, e_i);
+    if (a.vir_c) {
+      v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
+      v3 = warp_sum(v3); v4 = warp_sum(v4); v5 = warp_sum(v5);
+      if (lane == 0) {
+        double *vc = a.vir_c + (size_t) ii * 6;
+        vc[0] = v0; vc[1] = v1; vc[2] = v2; vc[3] = v3; vc[4] = v4; vc[5] = v5;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}    // namespace
+
+size_t annp_force_smem_bytes(const DevParams &hp, int capacity) {
+  const int nsf = hp.nsf, nl = hp.nlayers, nnod = hp.nnod;
+  size_t blk = (size_t) (hp.nelements * (hp.w_per_elem + hp.b_per_elem) + 2 * nsf) * sizeof(double);
+  blk = (blk + 15) & ~(size_t) 15;
+  size_t per_warp = ((size_t) 11 * capacity + 2 * hp.ntsf + 2 * hp.npsf + 2 * nsf + (size_t) 2 * nl * nnod + 2 * nnod) * sizeof(double) +
+                    (size_t) capacity * sizeof(int);
+  per_warp = (per_warp + 15) & ~(size_t) 15;
+  return blk + kWarps * per_warp;
+}
+
+typedef void (*force_kernel_t)(const ForceArgs);
+
+static force_kernel_t pick_kernel(int npsf, int ntsf) {
+  if (npsf == 9 && ntsf == 19) return annp_force_kernel<9, 19>;     // fe / fe_v2 potential
+  if (npsf == 8 && ntsf == 20) return annp_force_kernel<8, 20>;
+  if (npsf == 4 && ntsf == 6) return annp_force_kernel<4, 6>;       // small set used by unit tests
+  return nullptr;
+}
+
+bool annp_force_supported(int npsf, int ntsf) { return pick_kernel(npsf, ntsf) != nullptr; }
+
+// Launch on `stream`. grid_blocks <= 0 picks one full wave of resident blocks.
+cudaError_t annp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream,
+                              int *blocks_out) {
+  force_kernel_t k = pick_kernel(hp.npsf, hp.ntsf);
+  if (!k) return cudaErrorInvalidValue;
+  const size_t smem = annp_force_smem_bytes(hp, args.capacity);
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kWarps * 32, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorInvalidConfiguration;
+  long long want = ((long long) args.inum + kWarps - 1) / kWarps;
+  long long blocks = (long long) per_sm * num_sms;
+  if (blocks > want) blocks = want;
+  if (blocks < 1) blocks = 1;
+  if (blocks_out) *blocks_out = (int) blocks;
+  k<<<(unsigned) blocks, kWarps * 32, smem, stream>>>(args);
+  return cudaGetLastError();
+}

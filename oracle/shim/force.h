@@ -1,0 +1,7 @@
+#ifndef SHIM_FORCE_H
+#define SHIM_FORCE_H
+#include "pointers.h"
+namespace LAMMPS_NS {
+class Force { public: int newton_pair = 1; int newton = 1; };
+}
+#endif

@@ -1,0 +1,107 @@
+"""Generate the committed golden fixtures from the UNMODIFIED reference (run in the build container).
+
+    python tests/golden/make_golden.py
+
+Needs /root/reference and the binaries of `make -C oracle` (oracle/_ref/ref_*).  Writes
+  tests/golden/fe_potential.json   parameters of annp-gpu-lammps/fe_v2/fe_annp_potential_2.ann as parsed by
+                                   the reference-compatible reader (numbers round-trip exactly; the test
+                                   suite re-creates a `.ann` file from it with pair.write_potential)
+  tests/golden/annp_fe_*.npz       inputs (x, type, ghosts, neighbour rows) and the reference's outputs
+                                   (eng_vdwl, eatom, f, virial by pair tally and by f.r, vatom)
+  tests/golden/fe_st.npz           the 152 880-atom slab of `performance test.zip` + its logged thermo values
+The GPU box has no /root/reference: tests read only these files.
+"""
+import io
+import json
+import os
+import sys
+import zipfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from meng_zhang_b200 import lattice as L  # noqa: E402
+from meng_zhang_b200.pair import read_potential  # noqa: E402
+from oracle.run_ref import run_reference  # noqa: E402
+
+REF = "/root/reference"
+POT = f"{REF}/annp-gpu-lammps/fe_v2/fe_annp_potential_2.ann"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def dump_potential():
+    pot = read_potential(POT, ["Fe"])
+    d = {k: getattr(pot, k) for k in ("nelements", "ntl", "nhl", "nnod", "nsf", "npsf", "ntsf", "flagsym", "flagact",
+                                      "cut", "e_scale", "e_shift", "e_atom", "id_elem", "mass", "elements")}
+    d["sfnor_cov"] = pot.sfnor_cov.tolist()
+    d["sfnor_avg"] = pot.sfnor_avg.tolist()
+    d["weight_all"] = pot.weight_all.tolist()
+    d["bias_all"] = pot.bias_all.tolist()
+    d["source"] = "annp-gpu-lammps/fe_v2/fe_annp_potential_2.ann (MPL-2.0), parsed numbers only"
+    with open(os.path.join(OUT, "fe_potential.json"), "w") as fp:
+        json.dump(d, fp)
+
+
+def cases():
+    # name -> Config (+ element list)
+    out = {}
+    x, box = L.bcc(4, 4, 4)
+    out["bcc4_perfect"] = (L.build_config(x, box, 6.5), ["Fe"])
+    out["bcc4_perturbed"] = (L.build_config(L.perturb(x, 0.05, 12345), box, 6.5, shuffle_rows=7), ["Fe"])
+    x3, box3 = L.bcc(3, 3, 4)   # box edge 8.57 A: barely above the 8.5 A ghost cutoff, many self images
+    out["bcc334_hot"] = (L.build_config(L.perturb(x3, 0.15, 99), box3, 6.5, shuffle_rows=3), ["Fe"])
+    # free cluster: ragged rows, atoms with few or zero neighbours inside Rc, one isolated atom
+    xc, _ = L.bcc(3, 3, 3)
+    xc = L.perturb(xc, 0.08, 5)
+    xc = np.concatenate([xc, [[40.0, 40.0, 40.0]], [[46.0, 40.0, 40.0]], [[46.0, 44.5, 40.0]]])
+    out["cluster_ragged"] = (L.build_config(xc, np.array([100.0, 100.0, 100.0]), 6.5, periodic=(False, False, False)), ["Fe"])
+    # two LAMMPS types mapped to the same element (as the STGB generator's two grains)
+    rng = np.random.default_rng(11)
+    types = rng.integers(1, 3, size=128).astype(np.int32)
+    out["bcc4_two_types"] = (L.build_config(L.perturb(x, 0.05, 777), box, 6.5, types=types), ["Fe", "Fe"])
+    # BASELINE config 1 geometry: 10x10x10 cells = 2000 atoms
+    x10, box10 = L.bcc(10, 10, 10)
+    out["bcc10_perturbed"] = (L.build_config(L.perturb(x10, 0.05, 2024), box10, 6.5), ["Fe"])
+    return out
+
+
+def dump_cases():
+    for name, (cfg, elems) in cases().items():
+        r1 = run_reference("annp_fe", cfg, POT, elems, eflag=3, vflag=1 + 4)   # pair tally + per-atom virial
+        r2 = run_reference("annp_fe", cfg, POT, elems, eflag=3, vflag=2)       # virial through f.r
+        assert np.array_equal(r1["f"], r2["f"])
+        np.savez_compressed(
+            os.path.join(OUT, f"annp_fe_{name}.npz"),
+            nlocal=cfg.nlocal, nghost=cfg.nghost, x=cfg.x, type=cfg.type, ghost_owner=cfg.ghost_owner,
+            ilist=cfg.ilist, numneigh=cfg.numneigh, neigh=cfg.neigh, box=cfg.box, elements=np.array(elems),
+            eng_vdwl=r1["eng_vdwl"], eatom=r1["eatom"], f=r1["f"], virial_pair=r1["virial"], virial_fdotr=r2["virial"],
+            vatom=r1["vatom"], ref_seconds=r1["seconds"])
+        print(f"{name}: nlocal {cfg.nlocal} nghost {cfg.nghost} E/atom {r1['eng_vdwl'] / cfg.nlocal:.10f} "
+              f"fmax {np.abs(cfg.fold(r1['f'])).max():.6e} ({r1['seconds']:.1f} s)")
+
+
+def dump_fe_st():
+    z = zipfile.ZipFile(f"{REF}/annp-gpu-lammps/fe_v2/performance test.zip")
+    txt = z.read("performance comparsion/fe_st.dat").decode()
+    lines = txt.splitlines()
+    natoms = int(lines[1].split()[0])
+    box = np.array([[float(v) for v in lines[3 + d].split()[:2]] for d in range(3)])
+    start = next(i for i, l in enumerate(lines) if l.startswith("Atoms")) + 2
+    arr = np.loadtxt(io.StringIO("\n".join(lines[start:start + natoms])))
+    assert arr.shape == (natoms, 5)
+    order = np.argsort(arr[:, 0].astype(np.int64))
+    x = arr[order, 2:5]
+    # thermo values of the reference's own 2-GPU annp/gpu run (log_relaxing_new.lammps:109,117-120;
+    # log_relaxing_old.lammps:111,119-122); boundary m p m, 217.55887 neighbours/atom at 8.5 A
+    np.savez_compressed(os.path.join(OUT, "fe_st.npz"), x=x.astype(np.float64), box=box,
+                        e_pair_new=-684876292.365723, e_pair_old=-684876292.28418,
+                        fnorm_new=39.623051, fnorm_old=39.623117, fmax_new=0.93490135, fmax_old=0.93490485,
+                        press_new=-40423.638, press_old=-40426.438, volume=1773495.9, neighs_per_atom=217.55887)
+    print("fe_st:", natoms, box.tolist())
+
+
+if __name__ == "__main__":
+    dump_potential()
+    dump_fe_st()
+    dump_cases()
