@@ -11,7 +11,7 @@
  *   annp_b200_clear           <- annp_gpu_clear     src/pair_annp_gpu.cpp:41,   lib/lal_annp_ext.cpp:94-96
  *   annp_b200_bytes           <- annp_gpu_bytes     src/pair_annp_gpu.cpp:58,   lib/lal_annp_ext.cpp:121-123
  *   annp_b200_read_potential  <- PairANNP::read_file src/pair_annp.cpp:332-585 (potential file format)
- *   annp_b200_neigh_build / annp_b200_compute_device / annp_b200_nve_*  : the device-resident mode
+ *   annp_b200_neigh_build / annp_b200_compute_device / annp_b200_halo_* / annp_b200_nve_* : the device-resident mode
  *       (replaces the per-step H2D x / D2H f staging of lib/lal_annp.cpp:310-312,336-347 and the
  *        GPU_NEIGH path annp_gpu_compute_n, lib/lal_annp_ext.cpp:98-108)
  *
@@ -170,16 +170,21 @@ int annp_b200_compute_device(annp_b200_handle h, int nlocal, int nghost, const d
                              int eflag, int vflag, double *d_f, double *d_eatom, double *d_eng_virial,
                              double *d_vatom, void *stream);
 
-/* Ghosts that are periodic self-images of this rank's own atoms ("communication" inside one rank).
- * set_ghosts registers owner[g] (local index) and shift[g][3] of ghost g = nlocal + g and builds the
- * owner-major fold list once (call again after every re-neighbouring).  Device pointers; the arrays
- * must stay alive until the next set_ghosts.
- *   update_ghosts: x[nlocal+g] = x[owner[g]] + shift[g]             (forward)
- *   fold_ghosts  : f[owner[g]] += f[nlocal+g], in ascending g       (reverse, deterministic) */
-int annp_b200_set_ghosts(annp_b200_handle h, int nlocal, int nghost, const int *d_ghost_owner,
-                         const double *d_ghost_shift, void *stream);
-int annp_b200_update_ghosts(annp_b200_handle h, double *d_x, void *stream);
-int annp_b200_fold_ghosts(annp_b200_handle h, double *d_f, void *stream);
+/* Halo ("ghost") exchange for the device-resident mode: LAMMPS' forward / reverse communication
+ * (Comm::forward_comm / reverse_comm around Pair::compute) on device buffers.
+ *   set_halo registers the send list: entry m sends local atom send_index[m] displaced by
+ *   send_shift[m][3] (periodic image shift as seen by the receiver).  Entries are ordered by
+ *   destination rank, so the packed buffer can be handed to one grouped NCCL send/recv
+ *   (all_to_all_single); on one rank the "receiver" is this rank's own ghost block.  Device
+ *   pointers, which must stay alive until the next set_halo.
+ *     halo_pack        sendbuf[m] = x[send_index[m]] + send_shift[m]                    (forward)
+ *     halo_unpack_add  f[send_index[m]] += recvbuf[m], summed per atom in ascending m   (reverse;
+ *                      deterministic, no atomics).  recvbuf holds the ghost forces returned by
+ *                      the receivers in send order. */
+int annp_b200_set_halo(annp_b200_handle h, int nlocal, int nsend, const int *d_send_index,
+                       const double *d_send_shift, void *stream);
+int annp_b200_halo_pack(annp_b200_handle h, const double *d_x, double *d_sendbuf, void *stream);
+int annp_b200_halo_unpack_add(annp_b200_handle h, const double *d_recvbuf, double *d_f, void *stream);
 
 /* velocity-Verlet halves for the stand-alone MD loop (metal units; ftm2v = 1/(1.0364269e-4)):
  *   initial: v += dtf * f / m ; x += dt * v        final: v += dtf * f / m
@@ -204,6 +209,8 @@ typedef struct annp_b200_stats {
   long long kernel_launches; /* kernels launched by this handle so far     */
   float last_force_kernel_ms;/* CUDA-event time of the descriptor+force kernel of the last
                                 compute call issued with timing enabled, else 0 */
+  double force_kernel_ms_total; /* sum of the CUDA-event times of the force kernel over the (up to 256)  */
+  int force_kernel_samples;     /* ... timed launches since annp_b200_set_timing(h, 1)                    */
 } annp_b200_stats;
 int annp_b200_get_stats(annp_b200_handle h, annp_b200_stats *out);   /* synchronises the device */
 int annp_b200_set_timing(annp_b200_handle h, int enabled);

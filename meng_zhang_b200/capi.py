@@ -50,7 +50,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("inum", C.c_int), ("nall", C.c_int), ("max_neigh_list", C.c_int), ("max_neigh_cut", C.c_int),
         ("avg_neigh_cut", C.c_double), ("sum_triplets", C.c_double), ("kernel_launches", C.c_longlong),
-        ("last_force_kernel_ms", C.c_float),
+        ("last_force_kernel_ms", C.c_float), ("force_kernel_ms_total", C.c_double), ("force_kernel_samples", C.c_int),
     ]
 
 
@@ -73,9 +73,9 @@ PROTOTYPES = {
     "annp_b200_neigh_build": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, c_double_p, c_double_p, C.c_double, C.c_void_p]),
     "annp_b200_compute_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "annp_b200_set_ghosts": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "annp_b200_update_ghosts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "annp_b200_fold_ghosts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_set_halo": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_halo_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_halo_unpack_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_nve_initial": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_nve_final": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_fp64_peak_tflops": (C.c_double, [C.c_void_p, C.c_int]),

@@ -171,21 +171,25 @@ __global__ void k_reduce_ev_final(const double *__restrict__ partial, int nblock
 }
 
 // ---------------------------------------------------------------------------------------------
-// ghosts inside one rank (periodic self images) -- forward and reverse "communication"
-__global__ void k_update_ghosts(int nlocal, int nghost, const int *__restrict__ owner, const double *__restrict__ shift, double *__restrict__ x) {
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nghost; g += gridDim.x * blockDim.x) {
-    const int o = owner[g];
+// halo pack / unpack (forward and reverse communication buffers)
+__global__ void k_halo_pack(int nsend, const int *__restrict__ idx, const double *__restrict__ shift,
+                            const double *__restrict__ x, double *__restrict__ out) {
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < nsend; m += gridDim.x * blockDim.x) {
+    const size_t o = (size_t) idx[m];
 #pragma unroll
-    for (int k = 0; k < 3; k++) x[3 * (size_t) (nlocal + g) + k] = x[3 * (size_t) o + k] + shift[3 * (size_t) g + k];
+    for (int k = 0; k < 3; k++) out[3 * (size_t) m + k] = x[3 * o + k] + shift[3 * (size_t) m + k];
   }
 }
-// owner-major fold: thread per local atom walks its ghosts in ghost order (CSR built on the host side)
-__global__ void k_fold_ghosts_csr(int nlocal, const long long *__restrict__ goff, const int *__restrict__ glist, double *__restrict__ f) {
+// owner-major accumulate: thread per local atom walks its send entries in ascending order
+__global__ void k_halo_unpack_add(int nlocal, const long long *__restrict__ goff, const int *__restrict__ glist,
+                                  const double *__restrict__ src, double *__restrict__ f) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nlocal; i += gridDim.x * blockDim.x) {
+    const long long b = goff[i], e = goff[i + 1];
+    if (b == e) continue;
     double fx = f[3 * (size_t) i], fy = f[3 * (size_t) i + 1], fz = f[3 * (size_t) i + 2];
-    for (long long m = goff[i]; m < goff[i + 1]; m++) {
-      const size_t g = (size_t) nlocal + glist[m];
-      fx += f[3 * g]; fy += f[3 * g + 1]; fz += f[3 * g + 2];
+    for (long long m = b; m < e; m++) {
+      const size_t g = (size_t) glist[m];
+      fx += src[3 * g]; fy += src[3 * g + 1]; fz += src[3 * g + 2];
     }
     f[3 * (size_t) i] = fx; f[3 * (size_t) i + 1] = fy; f[3 * (size_t) i + 2] = fz;
   }
@@ -317,8 +321,8 @@ void aux_reduce_ev(const double4 *fself, const double *vir_c, int inum, double *
   k_reduce_ev_final<<<1, 32, 0, s>>>(partial, nb, out7);
 }
 
-void aux_update_ghosts(int nlocal, int nghost, const int *owner, const double *shift, double *x, cudaStream_t s) {
-  if (nghost > 0) k_update_ghosts<<<grid_for(nghost, 256), 256, 0, s>>>(nlocal, nghost, owner, shift, x);
+void aux_halo_pack(int nsend, const int *idx, const double *shift, const double *x, double *out, cudaStream_t s) {
+  if (nsend > 0) k_halo_pack<<<grid_for(nsend, 256), 256, 0, s>>>(nsend, idx, shift, x, out);
 }
 
 // builds (goff, glist): ghosts grouped by owner in ascending ghost order; scratch as for the reverse map
@@ -333,8 +337,8 @@ void aux_build_ghost_csr(const int *owner, int nghost, int nlocal, long long *go
     k_seg_sort<<<grid_for((long long) nlocal * 32, 256), 256, 0, s>>>(goff, tmp, glist, nlocal);
   }
 }
-void aux_fold_ghosts(int nlocal, const long long *goff, const int *glist, double *f, cudaStream_t s) {
-  if (nlocal > 0) k_fold_ghosts_csr<<<grid_for(nlocal, 256), 256, 0, s>>>(nlocal, goff, glist, f);
+void aux_halo_unpack_add(int nlocal, const long long *goff, const int *glist, const double *src, double *f, cudaStream_t s) {
+  if (nlocal > 0) k_halo_unpack_add<<<grid_for(nlocal, 256), 256, 0, s>>>(nlocal, goff, glist, src, f);
 }
 
 void aux_nve_initial(int n, double dt, double dtfm, double *x, double *v, const double *f, cudaStream_t s) {

@@ -27,10 +27,10 @@ void aux_gather_vatom(const double *vpair, const int *centre_of, const long long
 void aux_scatter_eatom(const double4 *fself, const int *ilist, int inum, double *eatom, cudaStream_t s);
 int aux_reduce_blocks(int inum);
 void aux_reduce_ev(const double4 *fself, const double *vir_c, int inum, double *partial, double *out7, cudaStream_t s);
-void aux_update_ghosts(int nlocal, int nghost, const int *owner, const double *shift, double *x, cudaStream_t s);
+void aux_halo_pack(int nsend, const int *idx, const double *shift, const double *x, double *out, cudaStream_t s);
 void aux_build_ghost_csr(const int *owner, int nghost, int nlocal, long long *goff, int *glist, int *cnt, int *tmp,
                          long long *tile_sum, cudaStream_t s);
-void aux_fold_ghosts(int nlocal, const long long *goff, const int *glist, double *f, cudaStream_t s);
+void aux_halo_unpack_add(int nlocal, const long long *goff, const int *glist, const double *src, double *f, cudaStream_t s);
 void aux_nve_initial(int n, double dt, double dtfm, double *x, double *v, const double *f, cudaStream_t s);
 void aux_nve_final(int n, double dtfm, double *v, const double *f, cudaStream_t s);
 int aux_ke_blocks(int n);
@@ -119,9 +119,12 @@ struct annp_b200_handle_s {
   bool need_calibrate = true;
   bool timing = false;
   bool debug_desc = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  static constexpr int kEvRing = 256;
+  cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
+  int ev_count = 0;                   // timed launches recorded and not yet collected
   float last_force_ms = 0.f;
-  bool ev_pending = false;
+  double force_ms_total = 0.0;
+  int force_samples = 0;
   long long launches = 0;
   DevCounters last_cnt;
   std::string err;
@@ -240,10 +243,11 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
   a.capacity = h->capacity;
 
   if (inum > 0) {
-    if (h->timing) { CK(cudaEventRecord(h->ev0, s)); }
+    const bool timed = h->timing && h->ev_count < annp_b200_handle_s::kEvRing;
+    if (timed) { CK(cudaEventRecord(h->ev0[h->ev_count], s)); }
     cudaError_t e = annp_force_launch(a, h->hp, h->num_sms, s, nullptr);
     if (e != cudaSuccess) return cuda_fail(h, e, "annp_force_launch");
-    if (h->timing) { CK(cudaEventRecord(h->ev1, s)); h->ev_pending = true; }
+    if (timed) { CK(cudaEventRecord(h->ev1[h->ev_count], s)); h->ev_count++; }
     h->launches += 1;
   }
   if (d_f) {
@@ -268,11 +272,16 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
 int fetch_counters(annp_b200_handle h, cudaStream_t s) {
   CK(cudaMemcpyAsync(&h->last_cnt, h->d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
-  if (h->ev_pending) {
-    cudaEventSynchronize(h->ev1);
-    cudaEventElapsedTime(&h->last_force_ms, h->ev0, h->ev1);
-    h->ev_pending = false;
+  for (int k = 0; k < h->ev_count; k++) {
+    float ms = 0.f;
+    cudaEventSynchronize(h->ev1[k]);
+    if (cudaEventElapsedTime(&ms, h->ev0[k], h->ev1[k]) == cudaSuccess) {
+      h->last_force_ms = ms;
+      h->force_ms_total += ms;
+      h->force_samples++;
+    }
   }
+  h->ev_count = 0;
   return ANNP_B200_OK;
 }
 
@@ -359,8 +368,10 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
   };
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
-  if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
-  if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+  for (int k = 0; k < annp_b200_handle_s::kEvRing; k++) {
+    if ((e = cudaEventCreate(&h->ev0[k])) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&h->ev1[k])) != cudaSuccess) return bail(e, "cudaEventCreate");
+  }
   const size_t wbytes = sizeof(double) * (size_t) hp.w_per_elem * p->nelements, bbytes = sizeof(double) * (size_t) hp.b_per_elem * p->nelements;
   if ((e = h->d_weights.reserve(wbytes, 1.0)) != cudaSuccess) return bail(e, "cudaMalloc weights");
   if ((e = h->d_bias.reserve(bbytes, 1.0)) != cudaSuccess) return bail(e, "cudaMalloc bias");
@@ -385,8 +396,10 @@ void annp_b200_clear(annp_b200_handle h) {
                     &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,
                     &h->d_eatom, &h->d_vatom, &h->d_goff, &h->d_glist, &h->d_ke_partial};
   for (DevBuf *b : bufs) b->release();
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int k = 0; k < annp_b200_handle_s::kEvRing; k++) {
+    if (h->ev0[k]) cudaEventDestroy(h->ev0[k]);
+    if (h->ev1[k]) cudaEventDestroy(h->ev1[k]);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -543,34 +556,34 @@ int annp_b200_neigh_build(annp_b200_handle h, int nlocal, int nall, const double
   return finish_list(h, s);
 }
 
-int annp_b200_set_ghosts(annp_b200_handle h, int nlocal, int nghost, const int *d_owner, const double *d_shift, void *stream) {
+int annp_b200_set_halo(annp_b200_handle h, int nlocal, int nsend, const int *d_index, const double *d_shift, void *stream) {
   if (!h) return ANNP_B200_EINVAL;
-  if (nlocal < 0 || nghost < 0 || (nghost > 0 && (!d_owner || !d_shift))) return fail(h, ANNP_B200_EINVAL, "bad ghost arguments");
+  if (nlocal < 0 || nsend < 0 || (nsend > 0 && (!d_index || !d_shift))) return fail(h, ANNP_B200_EINVAL, "bad halo arguments");
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t) stream;
-  h->g_nlocal = nlocal; h->g_nghost = nghost; h->g_owner = d_owner; h->g_shift = d_shift;
+  h->g_nlocal = nlocal; h->g_nghost = nsend; h->g_owner = d_index; h->g_shift = d_shift;
   CK(h->d_goff.reserve(sizeof(long long) * ((size_t) nlocal + 1)));
-  CK(h->d_glist.reserve(sizeof(int) * (size_t) std::max(nghost, 1)));
+  CK(h->d_glist.reserve(sizeof(int) * (size_t) std::max(nsend, 1)));
   CK(h->d_scratch_cnt.reserve(sizeof(int) * (size_t) std::max(nlocal, 1)));
-  CK(h->d_scratch_tmp.reserve(sizeof(int) * (size_t) std::max(nghost, 1)));
+  CK(h->d_scratch_tmp.reserve(sizeof(int) * (size_t) std::max(nsend, 1)));
   CK(h->d_tile_sum.reserve(sizeof(long long) * ((size_t) nlocal / 1024 + 2)));
-  aux_build_ghost_csr(d_owner, nghost, nlocal, h->d_goff.as<long long>(), h->d_glist.as<int>(), h->d_scratch_cnt.as<int>(),
+  aux_build_ghost_csr(d_index, nsend, nlocal, h->d_goff.as<long long>(), h->d_glist.as<int>(), h->d_scratch_cnt.as<int>(),
                       h->d_scratch_tmp.as<int>(), h->d_tile_sum.as<long long>(), s);
   h->launches += 7;
   CK(cudaGetLastError());
   return ANNP_B200_OK;
 }
 
-int annp_b200_update_ghosts(annp_b200_handle h, double *d_x, void *stream) {
-  if (!h || !d_x) return ANNP_B200_EINVAL;
-  aux_update_ghosts(h->g_nlocal, h->g_nghost, h->g_owner, h->g_shift, d_x, (cudaStream_t) stream);
+int annp_b200_halo_pack(annp_b200_handle h, const double *d_x, double *d_sendbuf, void *stream) {
+  if (!h || !d_x || (h->g_nghost > 0 && !d_sendbuf)) return ANNP_B200_EINVAL;
+  aux_halo_pack(h->g_nghost, h->g_owner, h->g_shift, d_x, d_sendbuf, (cudaStream_t) stream);
   h->launches += 1;
   return ANNP_B200_OK;
 }
 
-int annp_b200_fold_ghosts(annp_b200_handle h, double *d_f, void *stream) {
-  if (!h || !d_f) return ANNP_B200_EINVAL;
-  aux_fold_ghosts(h->g_nlocal, h->d_goff.as<long long>(), h->d_glist.as<int>(), d_f, (cudaStream_t) stream);
+int annp_b200_halo_unpack_add(annp_b200_handle h, const double *d_recvbuf, double *d_f, void *stream) {
+  if (!h || !d_f || (h->g_nghost > 0 && !d_recvbuf)) return ANNP_B200_EINVAL;
+  aux_halo_unpack_add(h->g_nlocal, h->d_goff.as<long long>(), h->d_glist.as<int>(), d_recvbuf, d_f, (cudaStream_t) stream);
   h->launches += 1;
   return ANNP_B200_OK;
 }
@@ -618,6 +631,8 @@ int annp_b200_get_stats(annp_b200_handle h, annp_b200_stats *out) {
   out->sum_triplets = (double) h->last_cnt.sum_trip;
   out->kernel_launches = h->launches;
   out->last_force_kernel_ms = h->last_force_ms;
+  out->force_kernel_ms_total = h->force_ms_total;
+  out->force_kernel_samples = h->force_samples;
   if (h->last_cnt.overflow) return fail(h, ANNP_B200_EOVERFLOW, "neighbour tile overflow in a device-mode step: results of that step are invalid");
   return ANNP_B200_OK;
 }
@@ -625,6 +640,9 @@ int annp_b200_get_stats(annp_b200_handle h, annp_b200_stats *out) {
 int annp_b200_set_timing(annp_b200_handle h, int enabled) {
   if (!h) return ANNP_B200_EINVAL;
   h->timing = enabled != 0;
+  h->force_ms_total = 0.0;
+  h->force_samples = 0;
+  h->ev_count = 0;
   return ANNP_B200_OK;
 }
 

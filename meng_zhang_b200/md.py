@@ -1,0 +1,282 @@
+"""Device-resident MD driver for the ANNP path (LAMMPS is not available in this image).
+
+Plays the role of LAMMPS' `Verlet::run` around `Pair::compute` for one rank per GPU
+(SURVEY.md section 3 C, section 8e): spatial brick decomposition of a periodic orthogonal box,
+ghost shell of `cutoff + skin`, forward communication of ghost positions and reverse communication of
+ghost forces every step, velocity-Verlet NVE.  Everything stays in HBM:
+
+    nve_initial -> halo_pack -> [NCCL all_to_all_single] -> compute_device -> [NCCL] -> halo_unpack_add -> nve_final
+
+The exchange is one grouped NCCL send/recv over NVLink per direction (torch.distributed is only the
+plumbing); with one rank the "exchange" is the pack kernel writing straight into the ghost block.
+PyTorch is used for device allocations, streams and the process group - all arithmetic is in
+libannp_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+
+import numpy as np
+import torch
+
+from . import capi
+
+KB = 8.617343e-5          # eV/K        (LAMMPS units metal: force->boltz)
+MVV2E = 1.0364269e-4      # (g/mol)(A/ps)^2 -> eV
+
+
+def decompose(nranks: int):
+    """1/2/4/8 -> 1x1x1 / 2x1x1 / 2x2x1 / 2x2x2; otherwise the most cubic factorisation."""
+    best = None
+    for px in range(1, nranks + 1):
+        if nranks % px:
+            continue
+        for py in range(1, nranks // px + 1):
+            if (nranks // px) % py:
+                continue
+            pz = nranks // px // py
+            key = (max(px, py, pz) - min(px, py, pz), -px, -py)
+            if best is None or key < best[0]:
+                best = (key, (px, py, pz))
+    return best[1]
+
+
+def rank_coords(rank, grid):
+    px, py, pz = grid
+    return (rank % px, (rank // px) % py, rank // (px * py))
+
+
+def coords_rank(c, grid):
+    px, py, pz = grid
+    return (c[0] % px) + (c[1] % py) * px + (c[2] % pz) * px * py
+
+
+def build_send_lists(x_local: np.ndarray, lo, hi, box, grid, coords, cutghost: float):
+    """Send entries for the 26 directions, grouped by destination rank.
+
+    Returns (index[int32 nsend], shift[nsend,3], send_counts[nranks]) with entries ordered by
+    destination rank and, inside one destination, by direction."""
+    nranks = grid[0] * grid[1] * grid[2]
+    for d in range(3):
+        if hi[d] - lo[d] < cutghost:
+            raise ValueError("sub-domain thinner than the ghost cutoff: multi-hop halo not supported")
+    per_dest = [[] for _ in range(nranks)]
+    for s in itertools.product((-1, 0, 1), repeat=3):
+        if s == (0, 0, 0):
+            continue
+        mask = np.ones(len(x_local), dtype=bool)
+        shift = np.zeros(3)
+        for d in range(3):
+            if s[d] == 1:
+                mask &= x_local[:, d] >= hi[d] - cutghost
+            elif s[d] == -1:
+                mask &= x_local[:, d] < lo[d] + cutghost
+            c = coords[d] + s[d]
+            if c >= grid[d]:
+                shift[d] = -box[d]
+            elif c < 0:
+                shift[d] = box[d]
+        idx = np.nonzero(mask)[0].astype(np.int32)
+        if len(idx):
+            dest = coords_rank([coords[d] + s[d] for d in range(3)], grid)
+            per_dest[dest].append((idx, shift))
+    index, shifts, counts = [], [], np.zeros(nranks, dtype=np.int64)
+    for dest in range(nranks):
+        for idx, shift in per_dest[dest]:
+            index.append(idx)
+            shifts.append(np.broadcast_to(shift, (len(idx), 3)))
+            counts[dest] += len(idx)
+    if index:
+        return np.concatenate(index), np.ascontiguousarray(np.concatenate(shifts)), counts
+    return np.zeros(0, dtype=np.int32), np.zeros((0, 3)), counts
+
+
+class DomainMD:
+    """One rank's sub-domain, device resident.  `pair` is an initialised PairANNPGPU."""
+
+    def __init__(self, pair, x_local, box, grid=(1, 1, 1), rank=0, device=None, type_local=None,
+                 skin=2.0, mass=55.845, dt=0.001, group=None):
+        self.pair = pair
+        self.L = capi.lib()
+        self.h = pair.handle
+        self.grid, self.rank = tuple(grid), rank
+        self.world = grid[0] * grid[1] * grid[2]
+        self.group = group
+        self.dev = torch.device(device if device is not None else "cuda")
+        self.box = np.asarray(box, dtype=np.float64)
+        self.coords = rank_coords(rank, self.grid)
+        self.lo = np.array([self.box[d] * self.coords[d] / self.grid[d] for d in range(3)])
+        self.hi = np.array([self.box[d] * (self.coords[d] + 1) / self.grid[d] for d in range(3)])
+        self.cut = pair.cutmax
+        self.skin, self.mass, self.dt = skin, mass, dt
+        self.nlocal = len(x_local)
+        self.nghost = 0
+        self._x_local0 = torch.as_tensor(np.ascontiguousarray(x_local), dtype=torch.float64, device=self.dev)
+        self._type_local = torch.ones(self.nlocal, dtype=torch.int32, device=self.dev) if type_local is None else \
+            torch.as_tensor(np.ascontiguousarray(type_local), dtype=torch.int32, device=self.dev)
+        self.v = torch.zeros((self.nlocal, 3), dtype=torch.float64, device=self.dev)
+        self.engvir = torch.zeros(8, dtype=torch.float64, device=self.dev)
+        self.ke = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self.x = self.f = self.type = None
+        self.nsteps = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise capi.AnnpError(rc, self.L.annp_b200_last_error(self.h).decode())
+
+    def set_velocities(self, temperature: float, seed: int):
+        """Gaussian velocities at `temperature`, zero net momentum (own RNG; the deck's
+        `velocity all create 300 4928459` uses LAMMPS' generator, in.st_test:29)."""
+        g = torch.Generator(device="cpu").manual_seed(seed + 7919 * self.rank)
+        sigma = (KB * temperature / (self.mass * MVV2E)) ** 0.5
+        v = torch.randn((self.nlocal, 3), generator=g, dtype=torch.float64) * sigma
+        v -= v.mean(dim=0, keepdim=True)
+        self.v = v.to(self.dev)
+
+    # ------------------------------------------------------------------ re-neighbouring (ago == 0)
+    def reneighbor(self):
+        """Rebuild send lists, ghosts and the device neighbour list from the current local positions."""
+        xl = (self.x[: self.nlocal] if self.x is not None else self._x_local0)
+        xl_host = xl.cpu().numpy()
+        cutghost = self.cut + self.skin
+        idx, shift, send_counts = build_send_lists(xl_host, self.lo, self.hi, self.box, self.grid, self.coords, cutghost)
+        self.send_counts = [int(c) for c in send_counts]
+        if self.world > 1:
+            import torch.distributed as dist
+            sc = torch.tensor(self.send_counts, dtype=torch.int64, device=self.dev)
+            rc = torch.empty_like(sc)
+            dist.all_to_all_single(rc, sc, group=self.group)
+            self.recv_counts = [int(c) for c in rc.cpu()]
+        else:
+            self.recv_counts = list(self.send_counts)
+        self.nsend = int(len(idx))
+        self.nghost = int(sum(self.recv_counts))
+        nall = self.nlocal + self.nghost
+        self.send_index = torch.as_tensor(idx, dtype=torch.int32, device=self.dev)
+        self.send_shift = torch.as_tensor(shift, dtype=torch.float64, device=self.dev)
+        x = torch.empty((nall, 3), dtype=torch.float64, device=self.dev)
+        x[: self.nlocal] = xl
+        self.x = x
+        self.f = torch.zeros((nall, 3), dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.sendbuf = torch.empty((self.nsend, 3), dtype=torch.float64, device=self.dev)
+            self.recvbuf = torch.empty((self.nsend, 3), dtype=torch.float64, device=self.dev)
+        self._ck(self.L.annp_b200_set_halo(self.h, self.nlocal, self.nsend, C.c_void_p(self.send_index.data_ptr()),
+                                           C.c_void_p(self.send_shift.data_ptr()), self._stream()))
+        # ghost types travel once per re-neighbouring
+        tl = self._type_local
+        if self.world > 1:
+            import torch.distributed as dist
+            tsend = tl[self.send_index.long()].contiguous()
+            tghost = torch.empty(self.nghost, dtype=torch.int32, device=self.dev)
+            dist.all_to_all_single(tghost, tsend, self.recv_counts, self.send_counts, group=self.group)
+        else:
+            tghost = tl[self.send_index.long()]
+        self.type = torch.cat([tl, tghost]).contiguous()
+        self.forward_comm()
+        lo = (self.lo - cutghost - 1e-6).astype(np.float64)
+        hi = (self.hi + cutghost + 1e-6).astype(np.float64)
+        # locals may have drifted slightly outside the brick between re-neighbourings
+        self._ck(self.L.annp_b200_neigh_build(self.h, self.nlocal, nall, C.c_void_p(self.x.data_ptr()),
+                                              lo.ctypes.data_as(capi.c_double_p), hi.ctypes.data_as(capi.c_double_p),
+                                              float(cutghost), self._stream()))
+
+    # ------------------------------------------------------------------ communication
+    def forward_comm(self):
+        """Ghost positions <- owners (Comm::forward_comm)."""
+        if self.nsend == 0 and self.nghost == 0:
+            return
+        if self.world == 1:
+            self._ck(self.L.annp_b200_halo_pack(self.h, C.c_void_p(self.x.data_ptr()),
+                                                C.c_void_p(self.x[self.nlocal:].data_ptr()), self._stream()))
+        else:
+            import torch.distributed as dist
+            self._ck(self.L.annp_b200_halo_pack(self.h, C.c_void_p(self.x.data_ptr()),
+                                                C.c_void_p(self.sendbuf.data_ptr()), self._stream()))
+            dist.all_to_all_single(self.x[self.nlocal:], self.sendbuf, self.recv_counts, self.send_counts, group=self.group)
+
+    def reverse_comm(self):
+        """Ghost forces -> owners, deterministic ordered accumulation (Comm::reverse_comm)."""
+        if self.nsend == 0 and self.nghost == 0:
+            return
+        if self.world == 1:
+            src = self.f[self.nlocal:]
+        else:
+            import torch.distributed as dist
+            dist.all_to_all_single(self.recvbuf, self.f[self.nlocal:], self.send_counts, self.recv_counts, group=self.group)
+            src = self.recvbuf
+        self._ck(self.L.annp_b200_halo_unpack_add(self.h, C.c_void_p(src.data_ptr()), C.c_void_p(self.f.data_ptr()), self._stream()))
+
+    # ------------------------------------------------------------------ force evaluation and integration
+    def compute(self, eflag=False, vflag=False):
+        self.forward_comm()
+        ev = C.c_void_p(self.engvir.data_ptr()) if (eflag or vflag) else None
+        self._ck(self.L.annp_b200_compute_device(self.h, self.nlocal, self.nghost, C.c_void_p(self.x.data_ptr()),
+                                                 C.c_void_p(self.type.data_ptr()), int(eflag), int(vflag),
+                                                 C.c_void_p(self.f.data_ptr()), None, ev, None, self._stream()))
+        self.reverse_comm()
+
+    def step(self, eflag=False):
+        """One velocity-Verlet step (FixNVE::initial_integrate, force, final_integrate)."""
+        s = self._stream()
+        self._ck(self.L.annp_b200_nve_initial(self.h, self.nlocal, self.dt, self.mass, C.c_void_p(self.x.data_ptr()),
+                                              C.c_void_p(self.v.data_ptr()), C.c_void_p(self.f.data_ptr()), s))
+        self.compute(eflag=eflag)
+        ke = C.c_void_p(self.ke.data_ptr()) if eflag else None
+        self._ck(self.L.annp_b200_nve_final(self.h, self.nlocal, self.dt, self.mass, C.c_void_p(self.v.data_ptr()),
+                                            C.c_void_p(self.f.data_ptr()), ke, s))
+        self.nsteps += 1
+
+    def thermo(self):
+        """(pe, ke) of the whole system in eV after a step(eflag=True)."""
+        t = torch.stack([self.engvir[0], self.ke[0]])
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.group)
+        pe, ke = t.cpu().tolist()
+        return pe, ke
+
+    def max_displacement_since(self, x_ref: torch.Tensor) -> float:
+        d = (self.x[: self.nlocal] - x_ref).norm(dim=1).max()
+        return float(d)
+
+    def run(self, nsteps: int, check_every: int = 5, thermo_every: int = 0, log=None):
+        """`run nsteps` with `neigh_modify every 5 delay 5 check yes` semantics (in.st_test:10-11):
+        every `check_every` steps re-neighbour if any atom moved more than skin/2 since the last build."""
+        if self.x is None:
+            self.reneighbor()
+            self.compute(eflag=True)
+        x_ref = self.x[: self.nlocal].clone()
+        rebuilds = 0
+        out = []
+        for n in range(1, nsteps + 1):
+            want_e = thermo_every > 0 and (n % thermo_every == 0 or n == nsteps)
+            s = self._stream()
+            self._ck(self.L.annp_b200_nve_initial(self.h, self.nlocal, self.dt, self.mass, C.c_void_p(self.x.data_ptr()),
+                                                  C.c_void_p(self.v.data_ptr()), C.c_void_p(self.f.data_ptr()), s))
+            if check_every > 0 and n % check_every == 0:
+                moved = (self.x[: self.nlocal] - x_ref).square().sum(dim=1).max()
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(moved, op=dist.ReduceOp.MAX, group=self.group)
+                if float(moved) > (0.5 * self.skin) ** 2:
+                    self.reneighbor()
+                    x_ref = self.x[: self.nlocal].clone()
+                    rebuilds += 1
+            self.compute(eflag=want_e)
+            ke = C.c_void_p(self.ke.data_ptr()) if want_e else None
+            self._ck(self.L.annp_b200_nve_final(self.h, self.nlocal, self.dt, self.mass, C.c_void_p(self.v.data_ptr()),
+                                                C.c_void_p(self.f.data_ptr()), ke, s))
+            self.nsteps += 1
+            if want_e:
+                pe, ke_v = self.thermo()
+                out.append((self.nsteps, pe, ke_v))
+                if log:
+                    log(self.nsteps, pe, ke_v)
+        self.rebuilds = rebuilds
+        return out

@@ -1,0 +1,73 @@
+"""The C-ABI library loads and exports every symbol include/annp_b200.h declares (no GPU needed)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from meng_zhang_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "annp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(annp_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(built):
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(built, n), f"{n} declared in include/annp_b200.h but not exported"
+
+
+def test_python_prototypes_cover_the_header(built):
+    assert set(capi.PROTOTYPES) == set(declared_symbols())
+
+
+def test_abi_version_and_sizes(built):
+    assert built.annp_b200_abi_version() == capi.ABI_VERSION
+    # Fe network 28-10-10-1: weights 280 + 100 + 10, biases 10 + 10 + 1
+    assert built.annp_b200_weights_per_element(4, 10, 28) == 390
+    assert built.annp_b200_bias_per_element(4, 10) == 21
+
+
+def test_library_is_built_for_sm_100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", capi.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_device_means_loud_failure_not_fallback(built, fe_pot_file):
+    """Without a GPU init must fail with ENODEVICE (the reference's -4 slot); nothing computes on the CPU."""
+    if built.annp_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    from meng_zhang_b200.pair import PairANNPGPU
+    from meng_zhang_b200.capi import AnnpError
+    pair = PairANNPGPU(ntypes=1)
+    pair.settings([])
+    pair.coeff(["*", "*", fe_pot_file, "Fe"])
+    with pytest.raises(AnnpError) as ei:
+        pair.init_style()
+    assert ei.value.code == capi.ENODEVICE
+    assert "no CPU fallback" in str(ei.value)
+
+
+def test_init_rejects_bad_parameter_blocks(built):
+    P = capi.Params()
+    h = C.c_void_p(None)
+    err = C.create_string_buffer(256)
+    P.abi_version = 999
+    assert built.annp_b200_init(C.byref(P), -1, 0, 0, C.byref(h), err, 256) == capi.EINVAL
+    assert b"ABI" in err.value
+    P.abi_version = capi.ABI_VERSION
+    P.ntypes, P.nelements, P.ntl, P.nnod, P.nsf, P.npsf, P.ntsf, P.flagsym = 1, 1, 4, 10, 28, 9, 19, 1
+    assert built.annp_b200_init(C.byref(P), -1, 0, 0, C.byref(h), err, 256) == capi.EINVAL
+    assert b"Chebyshev" in err.value
+    assert built.annp_b200_init(None, -1, 0, 0, C.byref(h), err, 256) == capi.EINVAL

@@ -1,0 +1,112 @@
+"""Host-side logic: potential reader/writer, pair-style argument handling, synthetic configurations."""
+import numpy as np
+import pytest
+
+import util
+from meng_zhang_b200 import lattice as L
+from meng_zhang_b200.pair import LammpsError, PairANNPGPU, read_potential, write_potential
+
+
+def test_reader_reproduces_the_reference_file_contract(fe_pot_file):
+    pot = read_potential(fe_pot_file, ["Fe"])
+    g = util.load_potential_json()
+    assert (pot.ntl, pot.nhl, pot.nnod, pot.nsf, pot.npsf, pot.ntsf) == (4, 2, 10, 28, 9, 19)
+    assert pot.cut == 6.5 and pot.flagsym == 0
+    assert pot.flagact == [4, 4, 0]          # "tanh" is matched by "ta" -> activation 4 (pair_annp.cpp:423)
+    assert pot.e_scale == 0.80684104305538540 and pot.e_shift == -1019.0781365280557 and pot.e_atom == -3460.0
+    assert pot.elements == ["Fe"] and pot.mass == [55.847]
+    assert np.array_equal(pot.weight_all, g.weight_all) and np.array_equal(pot.bias_all, g.bias_all)
+    assert np.array_equal(pot.sfnor_cov, g.sfnor_cov) and np.array_equal(pot.sfnor_avg, g.sfnor_avg)
+    # rows are padded to nsf columns like c_3d_matrix(n_lay, n_nod, n_sf) (pair_annp.cpp:445)
+    assert pot.weight_all.shape == (1, 3, 10, 28) and np.all(pot.weight_all[0, 1, :, 10:] == 0)
+    assert np.all(pot.weight_all[0, 2, 1:, :] == 0)
+
+
+def test_reader_tokenisation_quirks(tmp_path):
+    """Numbers are taken at column 0 and after TAB+digit/'-' only; CRLF is tolerated."""
+    pot = util.load_potential_json()
+    p = tmp_path / "q.ann"
+    write_potential(str(p), pot)
+    txt = open(p, newline="").read()
+    assert "\r\n" in txt
+    lines = txt.split("\r\n")
+    # a value written as ".5" after a tab is skipped by the reference scanner, shifting the row left
+    row = lines[12].split("\t")
+    row[1] = ".5"
+    lines[12] = "\t".join(row)
+    open(p, "w", newline="").write("\r\n".join(lines))
+    q = read_potential(str(p), ["Fe"])
+    assert q.sfnor_cov[0] == pot.sfnor_cov[0]
+    assert q.sfnor_cov[1] == pot.sfnor_cov[2]          # shifted
+    # LF-only files parse identically
+    open(p, "w", newline="").write("\n".join(txt.split("\r\n")))
+    r = read_potential(str(p), ["Fe"])
+    assert np.array_equal(r.weight_all, pot.weight_all) and r.flagact == pot.flagact
+
+
+def test_reader_errors(tmp_path):
+    with pytest.raises(LammpsError, match="Cannot open neural network potential file"):
+        read_potential(str(tmp_path / "missing.ann"), ["Fe"])
+    p = tmp_path / "short.ann"
+    p.write_text("#a\r\n#b\r\n")
+    with pytest.raises(LammpsError):
+        read_potential(str(p), ["Fe"])
+
+
+def test_sf_scale_matches_reference_formula():
+    pot = util.load_potential_json()
+    s = pot.sf_scale()
+    assert np.allclose(s, 1.0 / np.sqrt(pot.sfnor_cov - pot.sfnor_avg ** 2), rtol=0, atol=0)
+    pot.sfnor_cov[3] = pot.sfnor_avg[3] ** 2     # degenerate -> 0 with a warning in the reference
+    assert pot.sf_scale()[3] == 0.0
+
+
+def test_pair_style_argument_errors(fe_pot_file):
+    pair = PairANNPGPU(ntypes=1)
+    with pytest.raises(LammpsError, match="Illegal pair_style command"):
+        pair.settings(["1.0"])
+    pair.settings([])
+    with pytest.raises(LammpsError, match="Incorrect args for pair coefficients"):
+        pair.coeff(["*", "*", fe_pot_file])                 # missing element
+    with pytest.raises(LammpsError, match="Incorrect args for pair coefficients"):
+        pair.coeff(["1", "*", fe_pot_file, "Fe"])
+    pair2 = PairANNPGPU(ntypes=2)
+    with pytest.raises(LammpsError, match="Incorrect args for pair coefficients"):
+        pair2.coeff(["*", "*", fe_pot_file, "Fe", "Ni"])      # two elements, file has one
+    pair2.coeff(["*", "*", fe_pot_file, "Fe", "Fe"])
+    assert list(pair2.map) == [-1, 0, 0] and pair2.cutmax == 6.5
+    assert pair2.init_one(1, 2) == 6.5
+    off = PairANNPGPU(ntypes=1, newton_pair=0)
+    off.coeff(["*", "*", fe_pot_file, "Fe"])
+    with pytest.raises(LammpsError, match="requires newton pair on"):
+        off.init_style()
+
+
+def test_flat_weights_layout():
+    pot = util.load_potential_json()
+    w, b = pot.flat_weights()
+    assert w.size == 390 and b.size == 21
+    assert w[28 * 3 + 5] == pot.weight_all[0, 0, 3, 5]        # k + j*ncol (pair_annp_gpu.cpp:203)
+    assert w[280 + 10 * 2 + 7] == pot.weight_all[0, 1, 2, 7]
+    assert w[380 + 4] == pot.weight_all[0, 2, 0, 4]
+    assert b[20] == pot.bias_all[0, 2, 0]
+
+
+def test_bcc_neighbour_shells_and_ghosts():
+    x, box = L.bcc(4, 4, 4)
+    cfg = L.build_config(x, box, 6.5)
+    assert cfg.nlocal == 128
+    assert np.all(cfg.numneigh == 228)                       # 8.5 A list
+    off = cfg.offsets
+    d = np.linalg.norm(cfg.x[cfg.neigh[off[0]:off[1]]] - cfg.x[0], axis=1)
+    assert (d <= 6.5).sum() == 112                           # 112 in-cutoff neighbours
+    assert np.allclose(cfg.x[cfg.nlocal:], cfg.x[cfg.ghost_owner] + cfg.ghost_shift)
+    f = np.random.default_rng(0).normal(size=(cfg.nall, 3))
+    folded = cfg.fold(f)
+    assert np.allclose(folded.sum(axis=0), f.sum(axis=0))
+
+
+def test_free_boundaries_have_no_ghosts():
+    x, _ = L.bcc(2, 2, 2)
+    cfg = L.build_config(x + 10, np.array([50.0, 50, 50]), 6.5, periodic=(False, False, False))
+    assert cfg.nghost == 0 and cfg.numneigh.max() == 15

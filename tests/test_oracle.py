@@ -1,0 +1,86 @@
+"""The CPU oracle (oracle/annp_oracle.c) pinned against the reference.
+
+Golden vectors under tests/golden/ were produced by the UNMODIFIED reference pair style
+(annp-gpu-lammps/fe_v2/src/pair_annp.cpp compiled against oracle/shim, see make_golden.py).
+The restatement keeps the reference's operation order, so the comparison is bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import util
+from meng_zhang_b200 import lattice as L
+from meng_zhang_b200.pair import read_potential
+from oracle import restatement, run_ref
+
+
+@pytest.fixture(scope="module")
+def pot(fe_pot_file):
+    return read_potential(fe_pot_file, ["Fe"])
+
+
+@pytest.mark.parametrize("name", [c for c in util.FE_CASES if c != "bcc10_perturbed"])
+def test_restatement_matches_reference_golden_bit_exact(name, pot):
+    cfg, elems, ref = util.load_case(name)
+    out = restatement.compute(pot, cfg, ntypes=len(elems), vatom=True, nthreads=2)
+    assert out["eng_vdwl"] == ref["eng_vdwl"]
+    assert np.array_equal(out["eatom"], ref["eatom"])
+    assert np.array_equal(out["f"], ref["f"])
+    assert np.array_equal(out["virial"], ref["virial_pair"])
+    assert np.array_equal(out["vatom"], ref["vatom"])
+
+
+def test_restatement_2000_atoms_threads_do_not_change_bits(pot):
+    """BASELINE config 1 geometry; the OpenMP evaluation tallies in ilist order like the serial code."""
+    cfg, elems, ref = util.load_case("bcc10_perturbed")
+    out = restatement.compute(pot, cfg, nthreads=os.cpu_count() or 4)
+    assert out["eng_vdwl"] == ref["eng_vdwl"]
+    assert np.array_equal(out["f"], ref["f"])
+    assert np.array_equal(out["virial"], ref["virial_pair"])
+
+
+def test_golden_known_answers_of_the_survey_probe():
+    """Numbers the survey measured with the reference source: perfect bcc Fe."""
+    cfg, _, ref = util.load_case("bcc4_perfect")
+    assert abs(ref["eng_vdwl"] / cfg.nlocal - (-4479.8817655598)) < 1e-9
+    assert np.abs(cfg.fold(ref["f"])).max() < 1e-12
+    assert np.allclose(ref["virial_pair"][:3], -37.90672569, atol=1e-7)
+    assert np.allclose(ref["virial_fdotr"], ref["virial_pair"], atol=1e-10)
+
+
+@pytest.mark.skipif(not run_ref.available("annp_fe"), reason="oracle/_ref/ref_annp_fe not built")
+def test_restatement_matches_live_reference_on_a_fresh_configuration(pot, fe_pot_file):
+    x, box = L.bcc(3, 4, 5)
+    cfg = L.build_config(L.perturb(x, 0.1, 31337), box, 6.5, shuffle_rows=1)
+    ref = run_ref.run_reference("annp_fe", cfg, fe_pot_file, ["Fe"], eflag=3, vflag=1 + 4)
+    out = restatement.compute(pot, cfg, vatom=True)
+    assert out["eng_vdwl"] == ref["eng_vdwl"]
+    assert np.array_equal(out["f"], ref["f"])
+    assert np.array_equal(out["vatom"], ref["vatom"])
+
+
+def test_forces_are_the_energy_gradient(pot):
+    """Finite-difference self-consistency of the oracle (iii)."""
+    x, box = L.bcc(3, 3, 3)
+    x = L.perturb(x, 0.08, 5)
+    big = np.array([60.0, 60.0, 60.0])
+    cfg = L.build_config(x + 20.0, big, 6.5, periodic=(False, False, False))
+    base = restatement.compute(pot, cfg)
+    h = 1e-4
+    for atom, k in [(0, 0), (13, 1), (40, 2)]:
+        e = []
+        for s in (+1, -1):
+            xs = cfg.x.copy()
+            xs[atom, k] += s * h
+            c2 = L.Config(**{**cfg.__dict__, "x": xs})
+            e.append(restatement.compute(pot, c2)["eng_vdwl"])
+        fd = -(e[0] - e[1]) / (2 * h)
+        assert abs(fd - base["f"][atom, k]) < 5e-6, (atom, k, fd, base["f"][atom, k])
+
+
+def test_momentum_conservation_and_energy_sum(pot):
+    cfg, _, ref = util.load_case("bcc4_perturbed")
+    assert np.abs(ref["f"].sum(axis=0)).max() < 1e-11
+    assert abs(ref["eatom"][: cfg.nlocal].sum() - ref["eng_vdwl"]) < 1e-7
+    assert np.all(ref["eatom"][cfg.nlocal:] == 0.0)
