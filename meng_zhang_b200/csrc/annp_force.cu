@@ -4,20 +4,31 @@
 //   1. filters the LAMMPS list row to the in-cutoff neighbours (ballot compaction keeps list order),
 //      caches unit vector / fc / dfc / r per neighbour in shared memory and accumulates the radial
 //      Chebyshev sums                                   (reference: pair_annp.cpp:134-153, 633-656)
-//   2. walks every unordered neighbour pair (j,k) ONCE with a circulant schedule (lane <-> j,
-//      step <-> offset d, k = (j+d) mod N) and accumulates the 19 angular sums in registers
-//                                                       (reference: pair_annp.cpp:156-176, 658-695)
+//   2. walks every unordered neighbour pair (j,k) ONCE and accumulates the 19 angular sums in
+//      registers                                        (reference: pair_annp.cpp:156-176, 658-695)
 //   3. runs the element's MLP forward and reverse-mode backprop -> E_i and dE/dG
 //                                                       (reference: pair_annp.cpp:741-804)
 //   4. walks the pairs a second time, evaluating  A(y) = sum_n c_n T_n(y) and A'(y)  in the Chebyshev
 //      U basis (3 FMA per order) and accumulating, per neighbour, the five moments
 //          V = sum_k P u_k,  S = sum_k P cos(theta),  Aa = sum_k A fc_k     (P = A'/2 fc_j fc_k)
-//      j side in registers, k side by conflict-free shared-memory read-modify-write (all lanes of a
-//      step hit distinct k), so dG/dx is never materialised and no floating-point atomics are used
+//      so dG/dx is never materialised and no floating-point atomics are used
 //   5. turns the moments into the force on every neighbour, F_j = -e_scale dOut/dx_j
 //      (reference: pair_annp.cpp:191-200), writes it at the neighbour's LIST position (a later
 //      gather kernel sums them per atom in a fixed order), and reduces F_i = -sum F_j, the
 //      per-centre virial and the energy.
+//
+// Pair schedule of passes 2 and 4 ("row-pair circulant").  The N neighbours are padded to an even
+// count Np = 2M with a zero-weight dummy.  A lane owns the ROW PAIR (2m, 2m+1) and steps e = 1..M+1;
+// in step e it meets the single partner k = (2m + e) mod Np with both of its rows: triplet (2m, k)
+// has circulant offset e, triplet (2m+1, k) offset e-1, and offsets 1..M (the last one only for
+// rows < M) enumerate every unordered pair exactly once.  Consequences:
+//   * two independent Chebyshev recurrences per lane are in flight (latency hiding on the FP64 pipe)
+//   * the partner's data is loaded once, and its accumulators are updated once, per TWO triplets
+//   * rows are stored parity-split (even rows first), so the partners of consecutive lanes are
+//     consecutive shared-memory words: conflict-free 128-bit accesses, and all lanes of a step
+//     touch DISTINCT partners, which makes the plain read-modify-write race free and the
+//     summation order fixed (bit-reproducible results)
+//   * the step range is cut into Q segments so that M*Q work units fill the 32 lanes evenly.
 //
 // All arithmetic is IEEE FP64 (the reference CPU pair style is the parity target); the kernel is bound
 // by the FP64 FMA pipe, see DESIGN.md.
@@ -28,35 +39,56 @@ namespace {
 constexpr int kWarps = 4;            // warps per block; each warp is independent
 constexpr double kPi = 3.14159265358979323846;
 
-struct PassDesc {
-  int j, dlo, dhi, nsteps, group, splits;
+// One lane's work unit in a pass over the row pairs: row pair m, steps e = elo + t for t < nsteps.
+// Triplet 1 = (row 2m, partner) is valid for t < c1; triplet 2 = (row 2m+1, partner) for t2lo <= t < c2.
+struct Unit {
+  int m, elo, c1, c2, t2lo, seg;
   bool active;
 };
 
-// Work split of chunk c (32 lanes) of the N neighbour rows. Full chunks: lane <-> row, offsets 1..D.
-// The ragged tail chunk (R < 32 rows) splits the offset range over 2 or 4 lane groups so that all
-// lanes stay busy; groups are H >= R offsets apart, hence still hit distinct k in every step.
-__device__ __forceinline__ PassDesc make_pass(int c, int N, int D, int lane) {
-  PassDesc p;
-  const int base = c * 32;
-  const int R = N - base;
-  if (R >= 32) {
-    p.j = base + lane; p.dlo = 1; p.dhi = D; p.nsteps = D; p.group = 0; p.splits = 1; p.active = true;
-    return p;
+struct Sched {
+  int M;        // row pairs = padded neighbours / 2 = largest circulant offset
+  int Q;        // segments of the step range
+  int Hs;       // steps per segment
+  int npass;    // warp passes
+};
+
+__device__ __forceinline__ Sched make_sched(int Np) {
+  Sched sc;
+  sc.M = Np >> 1;
+  const int steps = sc.M + 1;
+  int bestQ = 1;
+  int best = ((sc.M + 31) >> 5) * steps;
+  if (sc.M >= 32) {
+#pragma unroll
+    for (int q = 2; q <= 8; q <<= 1) {
+      const int cost = ((sc.M * q + 31) >> 5) * ((steps + q - 1) / q) + q;   // + q: per-pass overhead
+      if (cost < best) { best = cost; bestQ = q; }
+    }
   }
-  int splits = 1;
-  if (N >= 64) splits = (R <= 8) ? 4 : ((R <= 16) ? 2 : 1);
-  const int rpad = 32 / splits;
-  const int g = lane / rpad, jr = lane - g * rpad;
-  const int H = (D + splits - 1) / splits;
-  p.active = jr < R;
-  p.j = base + jr;
-  p.dlo = 1 + g * H;
-  p.dhi = min(D, p.dlo + H - 1);
-  p.nsteps = H;
-  p.group = g;
-  p.splits = splits;
-  return p;
+  sc.Q = bestQ;
+  sc.Hs = (steps + bestQ - 1) / bestQ;
+  sc.npass = (sc.M * bestQ + 31) >> 5;
+  return sc;
+}
+
+__device__ __forceinline__ Unit make_unit(const Sched &sc, int pass, int lane) {
+  Unit u;
+  const int v = pass * 32 + lane;
+  const int M = sc.M;
+  u.active = v < M * sc.Q;
+  u.seg = v / M;
+  u.m = v - u.seg * M;
+  if (!u.active) { u.seg = 0; u.m = 0; }
+  u.elo = 1 + u.seg * sc.Hs;
+  const int ehi = min(M + 1, u.elo + sc.Hs - 1);
+  const int j1 = 2 * u.m, j2 = j1 + 1;
+  const int e1max = (j1 < M) ? M : M - 1;          // offset M only for rows < M
+  const int e2max = ((j2 < M) ? M : M - 1) + 1;    // triplet 2 has offset e - 1
+  u.c1 = u.active ? (min(ehi, e1max) - u.elo + 1) : 0;
+  u.c2 = u.active ? (min(ehi, e2max) - u.elo + 1) : 0;
+  u.t2lo = (u.elo == 1) ? 1 : 0;
+  return u;
 }
 
 __device__ __forceinline__ void activation(int flag, double z, double &h, double &hd) {
@@ -114,6 +146,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
   __syncthreads();
 
   const double two_over_cut = P.two_over_cut;
+  const int Ch = C >> 1;                  // rows are stored parity-split: even rows [0,Ch), odd rows [Ch,C)
+#define ROWPOS(r) ((((r) & 1) ? Ch : 0) + ((r) >> 1))
 
   for (;;) {
     unsigned long long item = 0;
@@ -156,12 +190,13 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         sincospi(r * rci, &sn, &cs);
         const double fc = 0.5 * (cs + 1.0);          // pair_annp.cpp:590-594
         const double dfc = -0.5 * kPi * rci * sn;
-        sA[slot] = make_double2(dx * rinv, dy * rinv);
-        sB[slot] = make_double2(dz * rinv, fc);
-        sC[slot] = make_double2(dfc, r);
-        accA[slot] = make_double2(0.0, 0.0);
-        accB[slot] = make_double2(0.0, 0.0);
-        accC[slot] = 0.0;
+        const int ps = ROWPOS(slot);
+        sA[ps] = make_double2(dx * rinv, dy * rinv);
+        sB[ps] = make_double2(dz * rinv, fc);
+        sC[ps] = make_double2(dfc, r);
+        accA[ps] = make_double2(0.0, 0.0);
+        accB[ps] = make_double2(0.0, 0.0);
+        accC[ps] = 0.0;
         spos[slot] = q;
         // radial Chebyshev sums, argument 2r/Rc - 1    (pair_annp.cpp:643-647)
         const double xr = r * two_over_cut - 1.0, xr2 = xr + xr;
@@ -189,49 +224,62 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       atomicAdd(&a.cnt->sum_neigh, (unsigned long long) N);
       atomicAdd(&a.cnt->sum_trip, (unsigned long long) N * (unsigned long long) (N > 0 ? N - 1 : 0) / 2ull);
     }
-    if (N > C) {   // capacity exceeded: flag it, emit zeros; the host re-runs with a larger tile
+    if (N + (N & 1) > C) {   // capacity exceeded: flag it, emit zeros; the host re-runs with a larger tile
       if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
       for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
       __syncwarp();
       continue;
     }
+    if ((N & 1) && lane == 0) {   // zero-weight dummy row pads N to an even count
+      const int ps = ROWPOS(N);
+      sA[ps] = make_double2(1.0, 0.0);
+      sB[ps] = make_double2(0.0, 0.0);
+      sC[ps] = make_double2(0.0, 1.0);
+      accA[ps] = make_double2(0.0, 0.0);
+      accB[ps] = make_double2(0.0, 0.0);
+      accC[ps] = 0.0;
+    }
     __syncwarp();
 
-    const int D = N >> 1;
-    const bool n_even = (N & 1) == 0;
-    const int nchunks = (N + 31) >> 5;
+    const Sched sch = make_sched(N + (N & 1));
+    const int M = sch.M;
 
     // ------------------------------------------------------------------ 2. angular sums (forward)
     double S[NTSF];
 #pragma unroll
     for (int n = 0; n < NTSF; n++) S[n] = 0.0;
-    for (int c = 0; c < nchunks; c++) {
-      const PassDesc ps = make_pass(c, N, D, lane);
-      double ujx = 0, ujy = 0, ujz = 0, fcj = 0;
-      if (ps.active) {
-        const double2 A = sA[ps.j], B = sB[ps.j];
-        ujx = A.x; ujy = A.y; ujz = B.x; fcj = B.y;
-      }
-      for (int t = 0; t < ps.nsteps; t++) {
-        const int d = ps.dlo + t;
-        const bool ok = ps.active && d <= ps.dhi && !(n_even && d == D && ps.j >= D);
-        if (ok) {
-          int k = ps.j + d;
-          if (k >= N) k -= N;
-          const double2 A = sA[k], B = sB[k];
-          const double y2 = fma(ujx, A.x, fma(ujy, A.y, fma(ujz, B.x, 1.0)));   // cos(theta) + 1
-          const double w = fcj * B.y;
-          const double y = 0.5 * y2;                                            // pair_annp.cpp:671
-          S[0] += w;
-          if (NTSF > 1) S[1] = fma(w, y, S[1]);
-          double t0 = 1.0, t1 = y;
+    for (int pass = 0; pass < sch.npass; pass++) {
+      const Unit un = make_unit(sch, pass, lane);
+      const double2 A1 = sA[un.m], B1 = sB[un.m], A2 = sA[Ch + un.m], B2 = sB[Ch + un.m];
+      // partner position: parity half of e, index (m + e/2) mod M
+      int e = un.elo;
+      int kc = un.m + (e >> 1);
+      if (kc >= M) kc -= M;
+      for (int t = 0; t < sch.Hs; t++) {
+        const int kp = ((e & 1) ? Ch : 0) + kc;
+        const double2 Ak = sA[kp], Bk = sB[kp];
+        const double f1 = (t < un.c1) ? B1.y : 0.0;
+        const double f2 = (t >= un.t2lo && t < un.c2) ? B2.y : 0.0;
+        const double y2a = fma(A1.x, Ak.x, fma(A1.y, Ak.y, fma(B1.x, Bk.x, 1.0)));   // cos(theta) + 1
+        const double y2b = fma(A2.x, Ak.x, fma(A2.y, Ak.y, fma(B2.x, Bk.x, 1.0)));
+        const double wa = f1 * Bk.y, wb = f2 * Bk.y;
+        const double ya = 0.5 * y2a, yb = 0.5 * y2b;                                   // pair_annp.cpp:671
+        S[0] += wa;
+        S[0] += wb;
+        if (NTSF > 1) { S[1] = fma(wa, ya, S[1]); S[1] = fma(wb, yb, S[1]); }
+        double ta0 = 1.0, ta1 = ya, tb0 = 1.0, tb1 = yb;
 #pragma unroll
-          for (int n = 2; n < NTSF; n++) {
-            const double tn = fma(y2, t1, -t0);
-            S[n] = fma(w, tn, S[n]);
-            t0 = t1; t1 = tn;
-          }
+        for (int n = 2; n < NTSF; n++) {
+          const double tan_ = fma(y2a, ta1, -ta0);
+          const double tbn_ = fma(y2b, tb1, -tb0);
+          S[n] = fma(wa, tan_, S[n]);
+          S[n] = fma(wb, tbn_, S[n]);
+          ta0 = ta1; ta1 = tan_;
+          tb0 = tb1; tb1 = tbn_;
         }
+        // next step: e + 1 flips the parity half; the index advances when e becomes even
+        e++;
+        if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
       }
     }
     // warp reduction (fixed butterfly order -> deterministic), scaling and centring (pair_annp.cpp:178-180)
@@ -321,57 +369,89 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     __syncwarp();
 
     // ------------------------------------------------------------------ 4. angular moments (backward)
-    for (int c = 0; c < nchunks; c++) {
-      const PassDesc ps = make_pass(c, N, D, lane);
-      double ujx = 0, ujy = 0, ujz = 0, fcj = 0;
-      if (ps.active) {
-        const double2 A = sA[ps.j], B = sB[ps.j];
-        ujx = A.x; ujy = A.y; ujz = B.x; fcj = B.y;
-      }
-      double vx = 0, vy = 0, vz = 0, ss = 0, aa = 0;
-      for (int t = 0; t < ps.nsteps; t++) {
-        const int d = ps.dlo + t;
-        const bool ok = ps.active && d <= ps.dhi && !(n_even && d == D && ps.j >= D);
-        if (ok) {
-          int k = ps.j + d;
-          if (k >= N) k -= N;
-          const double2 A = sA[k], B = sB[k];
-          const double ct = fma(ujx, A.x, fma(ujy, A.y, ujz * B.x));
-          const double y2 = ct + 1.0;                  // U_1(y) = 2y = cos(theta) + 1
-          double u0 = 1.0, u1 = y2;
-          const double2 q0 = coefT[0];
-          double Ay = q0.x, Apy = q0.y;
-          if (NTSF > 1) { const double2 q1 = coefT[1]; Ay = fma(q1.x, u1, Ay); Apy = fma(q1.y, u1, Apy); }
+    for (int pass = 0; pass < sch.npass; pass++) {
+      const Unit un = make_unit(sch, pass, lane);
+      // lanes of one pass may belong to two consecutive segments; their partners can coincide, so such a
+      // pass updates the partner accumulators in two phases (first segment, then second)
+      const int seg_first = __shfl_sync(0xffffffffu, un.seg, 0);
+      const bool straddle = __any_sync(0xffffffffu, un.active && un.seg != seg_first);
+      const bool phase0 = un.active && un.seg == seg_first, phase1 = un.active && un.seg != seg_first;
+      const double2 A1 = sA[un.m], B1 = sB[un.m], A2 = sA[Ch + un.m], B2 = sB[Ch + un.m];
+      double v1x = 0, v1y = 0, v1z = 0, s1 = 0, a1 = 0;
+      double v2x = 0, v2y = 0, v2z = 0, s2 = 0, a2 = 0;
+      int e = un.elo;
+      int kc = un.m + (e >> 1);
+      if (kc >= M) kc -= M;
+      for (int t = 0; t < sch.Hs; t++) {
+        const int kp = ((e & 1) ? Ch : 0) + kc;
+        const double2 Ak = sA[kp], Bk = sB[kp];
+        const bool ok1 = t < un.c1, ok2 = (t >= un.t2lo && t < un.c2);
+        const double f1 = ok1 ? B1.y : 0.0, f2 = ok2 ? B2.y : 0.0;      // fc_j, zero for idle slots
+        const double g1 = ok1 ? Bk.y : 0.0, g2 = ok2 ? Bk.y : 0.0;      // fc_k
+        const double cta = fma(A1.x, Ak.x, fma(A1.y, Ak.y, B1.x * Bk.x));
+        const double ctb = fma(A2.x, Ak.x, fma(A2.y, Ak.y, B2.x * Bk.x));
+        const double y2a = cta + 1.0, y2b = ctb + 1.0;                   // U_1(y) = 2y = cos(theta) + 1
+        double ua0 = 1.0, ua1 = y2a, ub0 = 1.0, ub1 = y2b;
+        const double2 q0 = coefT[0];
+        double Aa_ = q0.x, Apa = q0.y, Ab_ = q0.x, Apb = q0.y;
+        if (NTSF > 1) {
+          const double2 q1 = coefT[1];
+          Aa_ = fma(q1.x, ua1, Aa_); Apa = fma(q1.y, ua1, Apa);
+          Ab_ = fma(q1.x, ub1, Ab_); Apb = fma(q1.y, ub1, Apb);
+        }
 #pragma unroll
-          for (int n = 2; n < NTSF; n++) {
-            const double un = fma(y2, u1, -u0);
-            const double2 qn = coefT[n];
-            Ay = fma(qn.x, un, Ay);
-            if (n < NTSF - 1) Apy = fma(qn.y, un, Apy);
-            u0 = u1; u1 = un;
+        for (int n = 2; n < NTSF; n++) {
+          const double uan = fma(y2a, ua1, -ua0);
+          const double ubn = fma(y2b, ub1, -ub0);
+          const double2 qn = coefT[n];
+          Aa_ = fma(qn.x, uan, Aa_);
+          Ab_ = fma(qn.x, ubn, Ab_);
+          if (n < NTSF - 1) { Apa = fma(qn.y, uan, Apa); Apb = fma(qn.y, ubn, Apb); }
+          ua0 = ua1; ua1 = uan;
+          ub0 = ub1; ub1 = ubn;
+        }
+        const double Pa = Apa * (f1 * Bk.y), Pb = Apb * (f2 * Bk.y);
+        // row side (registers)
+        v1x = fma(Pa, Ak.x, v1x); v1y = fma(Pa, Ak.y, v1y); v1z = fma(Pa, Bk.x, v1z);
+        s1 = fma(Pa, cta, s1);
+        a1 = fma(Aa_, g1, a1);
+        v2x = fma(Pb, Ak.x, v2x); v2y = fma(Pb, Ak.y, v2y); v2z = fma(Pb, Bk.x, v2z);
+        s2 = fma(Pb, ctb, s2);
+        a2 = fma(Ab_, g2, a2);
+        // partner side: both triplets first, then ONE shared-memory update
+        const double kx = fma(Pa, A1.x, Pb * A2.x), ky = fma(Pa, A1.y, Pb * A2.y), kz = fma(Pa, B1.x, Pb * B2.x);
+        const double ks = fma(Pa, cta, Pb * ctb);
+        const double ka = fma(Aa_, f1, Ab_ * f2);
+        if (phase0) {
+          double2 pa = accA[kp], pb = accB[kp];
+          pa.x += kx; pa.y += ky; pb.x += kz; pb.y += ks;
+          accA[kp] = pa; accB[kp] = pb;
+          accC[kp] += ka;
+        }
+        if (straddle) {
+          __syncwarp();
+          if (phase1) {
+            double2 pa = accA[kp], pb = accB[kp];
+            pa.x += kx; pa.y += ky; pb.x += kz; pb.y += ks;
+            accA[kp] = pa; accB[kp] = pb;
+            accC[kp] += ka;
           }
-          const double Pw = Apy * (fcj * B.y);
-          // j side (registers)
-          vx = fma(Pw, A.x, vx); vy = fma(Pw, A.y, vy); vz = fma(Pw, B.x, vz);
-          ss = fma(Pw, ct, ss);
-          aa = fma(Ay, B.y, aa);
-          // k side (shared memory, distinct k per lane in this step)
-          double2 ka = accA[k], kb = accB[k];
-          double kc = accC[k];
-          ka.x = fma(Pw, ujx, ka.x); ka.y = fma(Pw, ujy, ka.y);
-          kb.x = fma(Pw, ujz, kb.x); kb.y = fma(Pw, ct, kb.y);
-          kc = fma(Ay, fcj, kc);
-          accA[k] = ka; accB[k] = kb; accC[k] = kc;
         }
         __syncwarp();
+        e++;
+        if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
       }
-      // flush the j side; lane groups of a split tail chunk share rows -> one group at a time
-      for (int g = 0; g < ps.splits; g++) {
-        if (ps.active && ps.group == g) {
-          double2 ja = accA[ps.j], jb = accB[ps.j];
-          ja.x += vx; ja.y += vy; jb.x += vz; jb.y += ss;
-          accA[ps.j] = ja; accB[ps.j] = jb;
-          accC[ps.j] += aa;
+      // flush the row side; the same row pair can sit in several lanes (segments) -> one segment at a time
+      for (int g = 0; g < sch.Q; g++) {
+        if (un.active && un.seg == g) {
+          double2 ja = accA[un.m], jb = accB[un.m];
+          ja.x += v1x; ja.y += v1y; jb.x += v1z; jb.y += s1;
+          accA[un.m] = ja; accB[un.m] = jb;
+          accC[un.m] += a1;
+          double2 oa = accA[Ch + un.m], ob = accB[Ch + un.m];
+          oa.x += v2x; oa.y += v2y; ob.x += v2z; ob.y += s2;
+          accA[Ch + un.m] = oa; accB[Ch + un.m] = ob;
+          accC[Ch + un.m] += a2;
         }
         __syncwarp();
       }
@@ -382,9 +462,10 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
     const double mes = -P.e_scale;
     for (int s = lane; s < N; s += 32) {
-      const double2 A = sA[s], B = sB[s], Cc = sC[s];
-      const double2 va = accA[s], vb = accB[s];
-      const double aa = accC[s];
+      const int ps = ROWPOS(s);
+      const double2 A = sA[ps], B = sB[ps], Cc = sC[ps];
+      const double2 va = accA[ps], vb = accB[ps];
+      const double aa = accC[ps];
       const double ux = A.x, uy = A.y, uz = B.x, fc = B.y, dfc = Cc.x, r = Cc.y;
       const double rinv = 1.0 / r;
       // radial polynomial R(x) = sum c_m T_m(x) and R'(x) in the U basis
@@ -395,11 +476,11 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       if (NPSF > 1) { const double2 q1 = coefR[1]; Rv = fma(q1.x, u1, Rv); Rp = fma(q1.y, u1, Rp); }
 #pragma unroll
       for (int m = 2; m < NPSF; m++) {
-        const double un = fma(x2, u1, -u0);
+        const double un_ = fma(x2, u1, -u0);
         const double2 qm = coefR[m];
-        Rv = fma(qm.x, un, Rv);
-        if (m < NPSF - 1) Rp = fma(qm.y, un, Rp);
-        u0 = u1; u1 = un;
+        Rv = fma(qm.x, un_, Rv);
+        if (m < NPSF - 1) Rp = fma(qm.y, un_, Rp);
+        u0 = u1; u1 = un_;
       }
       // d out / d x_j = g u_j - V / r       with dr/dx_j = -u_j, dcos/dx_j = (cos u_j - u_k)/r
       const double g = -(Rp * two_over_cut * fc + Rv * dfc) - dfc * aa + vb.y * rinv;
@@ -434,6 +515,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     }
     __syncwarp();
   }
+#undef ROWPOS
 }
 
 }    // namespace
