@@ -98,7 +98,7 @@ struct annp_b200_handle_s {
   int num_sms = 0;
   cudaStream_t stream = nullptr;      // host-mode stream
   DevParams hp;                       // host copy (weights/bias pointers are device pointers)
-  DevBuf d_params, d_weights, d_bias;
+  DevBuf d_params, d_weights, d_bias, d_cheb2mono;
   // neighbour list
   bool have_list = false;
   int inum = 0, nall_list = 0, max_row = 0;
@@ -380,6 +380,35 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
   if ((e = cudaMemcpy(h->d_bias.p, p->bias, bbytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload bias");
   hp.weights = h->d_weights.as<double>();
   hp.bias = h->d_bias.as<double>();
+  {
+    // T_n(y) with y = (z+1)/2 written in powers of z = cos(theta): the backward pass evaluates the angular
+    // polynomial and its derivative by Horner's rule in z.  All intermediate numbers are dyadic rationals
+    // that long double holds exactly for the supported orders.
+    const int nt = p->ntsf;
+    if (nt > 24) return bail(cudaErrorInvalidValue, "ntsf > 24 is not supported by the monomial conversion");
+    std::vector<long double> T((size_t) nt * nt, 0.0L), M((size_t) nt * nt, 0.0L);   // T[n][k]: coefficient of y^k
+    for (int n = 0; n < nt; n++) {
+      if (n == 0) T[0] = 1.0L;
+      else if (n == 1) T[(size_t) nt + 1] = 1.0L;
+      else
+        for (int k = 0; k < nt; k++)
+          T[(size_t) n * nt + k] = (k > 0 ? 2.0L * T[(size_t) (n - 1) * nt + k - 1] : 0.0L) - T[(size_t) (n - 2) * nt + k];
+    }
+    std::vector<long double> pw(nt, 0.0L), nx(nt, 0.0L);     // ((z+1)/2)^k in powers of z
+    pw[0] = 1.0L;
+    for (int k = 0; k < nt; k++) {
+      for (int n = 0; n < nt; n++)
+        for (int q = 0; q <= k; q++) M[(size_t) q * nt + n] += T[(size_t) n * nt + k] * pw[q];
+      std::fill(nx.begin(), nx.end(), 0.0L);
+      for (int q = 0; q <= k && q + 1 < nt; q++) { nx[q] += 0.5L * pw[q]; nx[q + 1] += 0.5L * pw[q]; }
+      pw = nx;
+    }
+    std::vector<double> Md((size_t) nt * nt);
+    for (size_t q = 0; q < Md.size(); q++) Md[q] = (double) M[q];
+    if ((e = h->d_cheb2mono.reserve(sizeof(double) * Md.size(), 1.0)) != cudaSuccess) return bail(e, "cudaMalloc cheb2mono");
+    if ((e = cudaMemcpy(h->d_cheb2mono.p, Md.data(), sizeof(double) * Md.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload cheb2mono");
+    hp.cheb2mono = h->d_cheb2mono.as<double>();
+  }
   if ((e = cudaMemcpy(h->d_params.p, &hp, sizeof(DevParams), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload params");
   memset(&h->last_cnt, 0, sizeof(h->last_cnt));
   *out = h;
@@ -390,7 +419,7 @@ void annp_b200_clear(annp_b200_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf *bufs[] = {&h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
+  DevBuf *bufs[] = {&h->d_cheb2mono, &h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
                     &h->d_centre_of, &h->d_scratch_cnt, &h->d_scratch_tmp, &h->d_tile_sum, &h->d_cell_of, &h->d_cell_cnt,
                     &h->d_cell_off, &h->d_cell_atoms, &h->d_row_cnt, &h->d_small, &h->d_xq, &h->d_fpair, &h->d_fself, &h->d_vir_c,
                     &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,
@@ -406,7 +435,7 @@ void annp_b200_clear(annp_b200_handle h) {
 
 double annp_b200_bytes(annp_b200_handle h) {
   if (!h) return 0.0;
-  const DevBuf *bufs[] = {&h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
+  const DevBuf *bufs[] = {&h->d_cheb2mono, &h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
                           &h->d_centre_of, &h->d_scratch_cnt, &h->d_scratch_tmp, &h->d_tile_sum, &h->d_cell_of, &h->d_cell_cnt,
                           &h->d_cell_off, &h->d_cell_atoms, &h->d_row_cnt, &h->d_small, &h->d_xq, &h->d_fpair, &h->d_fself, &h->d_vir_c,
                           &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,

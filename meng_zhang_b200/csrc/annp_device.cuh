@@ -23,6 +23,8 @@ struct DevParams {
   // weights / biases follow in separate device arrays
   const double *weights;
   const double *bias;
+  // [ntsf][ntsf] row-major: monomial coefficient a_k (in z = cos theta) of T_n((z+1)/2) is cheb2mono[k*ntsf+n]
+  const double *cheb2mono;
 };
 
 // counters written by the force kernel (one block of 8 x 8 bytes)

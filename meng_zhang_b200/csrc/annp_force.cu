@@ -8,8 +8,9 @@
 //      registers                                        (reference: pair_annp.cpp:156-176, 658-695)
 //   3. runs the element's MLP forward and reverse-mode backprop -> E_i and dE/dG
 //                                                       (reference: pair_annp.cpp:741-804)
-//   4. walks the pairs a second time, evaluating  A(y) = sum_n c_n T_n(y) and A'(y)  in the Chebyshev
-//      U basis (3 FMA per order) and accumulating, per neighbour, the five moments
+//   4. walks the pairs a second time, evaluating  A(y) = sum_n c_n T_n(y) and A'(y)  by Horner's rule in
+//      z = cos(theta) (2 FMA per order; c is converted to monomial coefficients once per atom) and
+//      accumulating, per neighbour, the five moments
 //          V = sum_k P u_k,  S = sum_k P cos(theta),  Aa = sum_k A fc_k     (P = A'/2 fc_j fc_k)
 //      so dG/dx is never materialised and no floating-point atomics are used
 //   5. turns the moments into the force on every neighbour, F_j = -e_scale dOut/dx_j
@@ -118,10 +119,12 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
   double *sBias = sW + wtot;
   double *sScale = sBias + btot;
   double *sAvg = sScale + nsf;
-  double *blk_end = sAvg + nsf;
+  double *sC2M = sAvg + nsf;                          // [NTSF][NTSF] Chebyshev -> monomial(z) matrix
+  double *blk_end = sC2M + NTSF * NTSF;
   for (int t = threadIdx.x; t < wtot; t += blockDim.x) sW[t] = P.weights[t];
   for (int t = threadIdx.x; t < btot; t += blockDim.x) sBias[t] = P.bias[t];
   for (int t = threadIdx.x; t < nsf; t += blockDim.x) { sScale[t] = P.sf_scale[t]; sAvg[t] = P.sf_avg[t]; }
+  for (int t = threadIdx.x; t < NTSF * NTSF; t += blockDim.x) sC2M[t] = P.cheb2mono[t];
 
   // ---- per-warp region
   const size_t per_warp_doubles = (size_t) 11 * C + 2 * NTSF + 2 * NPSF + 2 * nsf + (size_t) 2 * nl * nnod + 2 * nnod;
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
   double2 *accA = sC + C;                             // Vx, Vy
   double2 *accB = accA + C;                           // Vz, S
   double *accC = reinterpret_cast<double *>(accB + C);   // Aa
-  double2 *coefT = reinterpret_cast<double2 *>(accC + C);   // angular (d_n, e_n) in the U basis
+  double2 *coefT = reinterpret_cast<double2 *>(accC + C);   // angular polynomial: NTSF monomial coefficients a_k (as doubles)
   double2 *coefR = coefT + NTSF;                      // radial  (d_m, e_m)
   double *sG = reinterpret_cast<double *>(coefR + NPSF);
   double *sdE = sG + nsf;
@@ -260,22 +263,36 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         const double2 Ak = sA[kp], Bk = sB[kp];
         const double f1 = (t < un.c1) ? B1.y : 0.0;
         const double f2 = (t >= un.t2lo && t < un.c2) ? B2.y : 0.0;
-        const double y2a = fma(A1.x, Ak.x, fma(A1.y, Ak.y, fma(B1.x, Bk.x, 1.0)));   // cos(theta) + 1
-        const double y2b = fma(A2.x, Ak.x, fma(A2.y, Ak.y, fma(B2.x, Bk.x, 1.0)));
-        const double wa = f1 * Bk.y, wb = f2 * Bk.y;
-        const double ya = 0.5 * y2a, yb = 0.5 * y2b;                                   // pair_annp.cpp:671
-        S[0] += wa;
-        S[0] += wb;
-        if (NTSF > 1) { S[1] = fma(wa, ya, S[1]); S[1] = fma(wb, yb, S[1]); }
-        double ta0 = 1.0, ta1 = ya, tb0 = 1.0, tb1 = yb;
+        // Z_n = w T_n(y) obeys the same recurrence as T_n, so the 19 sums take one DFMA (recurrence) and one
+        // DADD (accumulate) per order: with the operand-reuse cache that is 4 register reads per order,
+        // which is what the FP64 pipe can issue; a 3-register DFMA per accumulate would cost 5.
+        // The two triplets of the step run one after the other (both add into S[]), so consecutive
+        // instructions share operands.
+        {
+          const double y2 = fma(A1.x, Ak.x, fma(A1.y, Ak.y, fma(B1.x, Bk.x, 1.0)));   // cos(theta) + 1 = 2y (pair_annp.cpp:671)
+          double z0 = f1 * Bk.y;
+          double z1 = (0.5 * y2) * z0;
+          S[0] += z0;
+          if (NTSF > 1) S[1] += z1;
 #pragma unroll
-        for (int n = 2; n < NTSF; n++) {
-          const double tan_ = fma(y2a, ta1, -ta0);
-          const double tbn_ = fma(y2b, tb1, -tb0);
-          S[n] = fma(wa, tan_, S[n]);
-          S[n] = fma(wb, tbn_, S[n]);
-          ta0 = ta1; ta1 = tan_;
-          tb0 = tb1; tb1 = tbn_;
+          for (int n = 2; n < NTSF; n++) {
+            const double zn = fma(y2, z1, -z0);
+            S[n] += zn;
+            z0 = z1; z1 = zn;
+          }
+        }
+        {
+          const double y2 = fma(A2.x, Ak.x, fma(A2.y, Ak.y, fma(B2.x, Bk.x, 1.0)));
+          double z0 = f2 * Bk.y;
+          double z1 = (0.5 * y2) * z0;
+          S[0] += z0;
+          if (NTSF > 1) S[1] += z1;
+#pragma unroll
+          for (int n = 2; n < NTSF; n++) {
+            const double zn = fma(y2, z1, -z0);
+            S[n] += zn;
+            z0 = z1; z1 = zn;
+          }
         }
         // next step: e + 1 flips the parity half; the index advances when e becomes even
         e++;
@@ -350,13 +367,13 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     // Chebyshev-T coefficients c_n = s_n dOut/dG_n  ->  U-basis coefficients
     //   sum c_n T_n = sum d_n U_n,  d_0 = c_0 - c_2/2, d_n = (c_n - c_{n+2})/2
     //   d/dy sum c_n T_n = sum_{m} (m+1) c_{m+1} U_m        (angular e_m carries the reference's 1/2)
+    // angular: p(z) = sum_k a_k z^k = sum_n c_n T_n((z+1)/2),  a = C2M c   (then A = p, A'/2 = dp/dz)
+    double *aK = reinterpret_cast<double *>(coefT);
     if (lane < NTSF) {
-      const int n = lane;
-      const double c0 = sdE[NPSF + n] * sScale[NPSF + n];
-      const double c1 = (n + 1 < NTSF) ? sdE[NPSF + n + 1] * sScale[NPSF + n + 1] : 0.0;
-      const double c2 = (n + 2 < NTSF) ? sdE[NPSF + n + 2] * sScale[NPSF + n + 2] : 0.0;
-      const double dn = (n == 0) ? (c0 - 0.5 * c2) : 0.5 * (c0 - c2);
-      coefT[n] = make_double2(dn, 0.5 * (double) (n + 1) * c1);
+      double acc = 0.0;
+#pragma unroll
+      for (int n = 0; n < NTSF; n++) acc = fma(sC2M[lane * NTSF + n], sdE[NPSF + n] * sScale[NPSF + n], acc);
+      aK[lane] = acc;
     }
     if (lane < NPSF) {
       const int n = lane;
@@ -390,25 +407,15 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         const double g1 = ok1 ? Bk.y : 0.0, g2 = ok2 ? Bk.y : 0.0;      // fc_k
         const double cta = fma(A1.x, Ak.x, fma(A1.y, Ak.y, B1.x * Bk.x));
         const double ctb = fma(A2.x, Ak.x, fma(A2.y, Ak.y, B2.x * Bk.x));
-        const double y2a = cta + 1.0, y2b = ctb + 1.0;                   // U_1(y) = 2y = cos(theta) + 1
-        double ua0 = 1.0, ua1 = y2a, ub0 = 1.0, ub1 = y2b;
-        const double2 q0 = coefT[0];
-        double Aa_ = q0.x, Apa = q0.y, Ab_ = q0.x, Apb = q0.y;
-        if (NTSF > 1) {
-          const double2 q1 = coefT[1];
-          Aa_ = fma(q1.x, ua1, Aa_); Apa = fma(q1.y, ua1, Apa);
-          Ab_ = fma(q1.x, ub1, Ab_); Apb = fma(q1.y, ub1, Apb);
-        }
+        // Horner with derivative in z = cos(theta):  d <- d z + b ; b <- b z + a_k   (A = b, A'(y)/2 = d)
+        double Aa_ = aK[NTSF - 1], Apa = 0.0, Ab_ = Aa_, Apb = 0.0;
 #pragma unroll
-        for (int n = 2; n < NTSF; n++) {
-          const double uan = fma(y2a, ua1, -ua0);
-          const double ubn = fma(y2b, ub1, -ub0);
-          const double2 qn = coefT[n];
-          Aa_ = fma(qn.x, uan, Aa_);
-          Ab_ = fma(qn.x, ubn, Ab_);
-          if (n < NTSF - 1) { Apa = fma(qn.y, uan, Apa); Apb = fma(qn.y, ubn, Apb); }
-          ua0 = ua1; ua1 = uan;
-          ub0 = ub1; ub1 = ubn;
+        for (int k = NTSF - 2; k >= 0; k--) {
+          const double ak = aK[k];
+          Apa = fma(Apa, cta, Aa_);
+          Aa_ = fma(Aa_, cta, ak);
+          Apb = fma(Apb, ctb, Ab_);
+          Ab_ = fma(Ab_, ctb, ak);
         }
         const double Pa = Apa * (f1 * Bk.y), Pb = Apb * (f2 * Bk.y);
         // row side (registers)
@@ -418,23 +425,24 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         v2x = fma(Pb, Ak.x, v2x); v2y = fma(Pb, Ak.y, v2y); v2z = fma(Pb, Bk.x, v2z);
         s2 = fma(Pb, ctb, s2);
         a2 = fma(Ab_, g2, a2);
-        // partner side: both triplets first, then ONE shared-memory update
-        const double kx = fma(Pa, A1.x, Pb * A2.x), ky = fma(Pa, A1.y, Pb * A2.y), kz = fma(Pa, B1.x, Pb * B2.x);
-        const double ks = fma(Pa, cta, Pb * ctb);
-        const double ka = fma(Aa_, f1, Ab_ * f2);
+        // partner side: ONE shared-memory read-modify-write for both triplets
         if (phase0) {
           double2 pa = accA[kp], pb = accB[kp];
-          pa.x += kx; pa.y += ky; pb.x += kz; pb.y += ks;
-          accA[kp] = pa; accB[kp] = pb;
-          accC[kp] += ka;
+          double pc = accC[kp];
+          pa.x = fma(Pa, A1.x, pa.x); pa.y = fma(Pa, A1.y, pa.y); pb.x = fma(Pa, B1.x, pb.x); pb.y = fma(Pa, cta, pb.y);
+          pa.x = fma(Pb, A2.x, pa.x); pa.y = fma(Pb, A2.y, pa.y); pb.x = fma(Pb, B2.x, pb.x); pb.y = fma(Pb, ctb, pb.y);
+          pc = fma(Aa_, f1, pc); pc = fma(Ab_, f2, pc);
+          accA[kp] = pa; accB[kp] = pb; accC[kp] = pc;
         }
         if (straddle) {
           __syncwarp();
           if (phase1) {
             double2 pa = accA[kp], pb = accB[kp];
-            pa.x += kx; pa.y += ky; pb.x += kz; pb.y += ks;
-            accA[kp] = pa; accB[kp] = pb;
-            accC[kp] += ka;
+            double pc = accC[kp];
+            pa.x = fma(Pa, A1.x, pa.x); pa.y = fma(Pa, A1.y, pa.y); pb.x = fma(Pa, B1.x, pb.x); pb.y = fma(Pa, cta, pb.y);
+            pa.x = fma(Pb, A2.x, pa.x); pa.y = fma(Pb, A2.y, pa.y); pb.x = fma(Pb, B2.x, pb.x); pb.y = fma(Pb, ctb, pb.y);
+            pc = fma(Aa_, f1, pc); pc = fma(Ab_, f2, pc);
+            accA[kp] = pa; accB[kp] = pb; accC[kp] = pc;
           }
         }
         __syncwarp();
@@ -522,7 +530,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
 
 size_t annp_force_smem_bytes(const DevParams &hp, int capacity) {
   const int nsf = hp.nsf, nl = hp.nlayers, nnod = hp.nnod;
-  size_t blk = (size_t) (hp.nelements * (hp.w_per_elem + hp.b_per_elem) + 2 * nsf) * sizeof(double);
+  size_t blk = (size_t) (hp.nelements * (hp.w_per_elem + hp.b_per_elem) + 2 * nsf + hp.ntsf * hp.ntsf) * sizeof(double);
   blk = (blk + 15) & ~(size_t) 15;
   size_t per_warp = ((size_t) 11 * capacity + 2 * hp.ntsf + 2 * hp.npsf + 2 * nsf + (size_t) 2 * nl * nnod + 2 * nnod) * sizeof(double) +
                     (size_t) capacity * sizeof(int);
