@@ -63,12 +63,16 @@ __device__ __forceinline__ Sched make_sched(int Np) {
   if (sc.M >= 32) {
 #pragma unroll
     for (int q = 2; q <= 8; q <<= 1) {
-      const int cost = ((sc.M * q + 31) >> 5) * ((steps + q - 1) / q) + q;   // + q: per-pass overhead
+      const int cost = ((sc.M * q + 31) >> 5) * (((steps + q - 1) / q) | 1) + q;   // + q: per-pass overhead
       if (cost < best) { best = cost; bestQ = q; }
     }
   }
   sc.Q = bestQ;
   sc.Hs = (steps + bestQ - 1) / bestQ;
+  // lanes of one pass can belong to two consecutive segments (never more: Q > 1 needs M >= 32).  With an
+  // ODD segment length their step numbers differ in parity, so they address different parity halves of
+  // the row arrays and can never meet at the same partner.
+  if (bestQ > 1) sc.Hs |= 1;
   sc.npass = (sc.M * bestQ + 31) >> 5;
   return sc;
 }
@@ -258,9 +262,13 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       int e = un.elo;
       int kc = un.m + (e >> 1);
       if (kc >= M) kc -= M;
+      double2 Ak = sA[((e & 1) ? Ch : 0) + kc], Bk = sB[((e & 1) ? Ch : 0) + kc];
       for (int t = 0; t < sch.Hs; t++) {
-        const int kp = ((e & 1) ? Ch : 0) + kc;
-        const double2 Ak = sA[kp], Bk = sB[kp];
+        // next step: e + 1 flips the parity half; the index advances when e becomes even (prefetch)
+        e++;
+        if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
+        const int kpn = ((e & 1) ? Ch : 0) + kc;
+        const double2 Akn = sA[kpn], Bkn = sB[kpn];
         const double f1 = (t < un.c1) ? B1.y : 0.0;
         const double f2 = (t >= un.t2lo && t < un.c2) ? B2.y : 0.0;
         // Z_n = w T_n(y) obeys the same recurrence as T_n, so the 19 sums take one DFMA (recurrence) and one
@@ -294,9 +302,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
             z0 = z1; z1 = zn;
           }
         }
-        // next step: e + 1 flips the parity half; the index advances when e becomes even
-        e++;
-        if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
+        Ak = Akn; Bk = Bkn;
       }
     }
     // warp reduction (fixed butterfly order -> deterministic), scaling and centring (pair_annp.cpp:178-180)
@@ -388,20 +394,23 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     // ------------------------------------------------------------------ 4. angular moments (backward)
     for (int pass = 0; pass < sch.npass; pass++) {
       const Unit un = make_unit(sch, pass, lane);
-      // lanes of one pass may belong to two consecutive segments; their partners can coincide, so such a
-      // pass updates the partner accumulators in two phases (first segment, then second)
-      const int seg_first = __shfl_sync(0xffffffffu, un.seg, 0);
-      const bool straddle = __any_sync(0xffffffffu, un.active && un.seg != seg_first);
-      const bool phase0 = un.active && un.seg == seg_first, phase1 = un.active && un.seg != seg_first;
       const double2 A1 = sA[un.m], B1 = sB[un.m], A2 = sA[Ch + un.m], B2 = sB[Ch + un.m];
       double v1x = 0, v1y = 0, v1z = 0, s1 = 0, a1 = 0;
       double v2x = 0, v2y = 0, v2z = 0, s2 = 0, a2 = 0;
       int e = un.elo;
       int kc = un.m + (e >> 1);
       if (kc >= M) kc -= M;
+      int kp = ((e & 1) ? Ch : 0) + kc;
+      double2 Ak = sA[kp], Bk = sB[kp];
       for (int t = 0; t < sch.Hs; t++) {
-        const int kp = ((e & 1) ? Ch : 0) + kc;
-        const double2 Ak = sA[kp], Bk = sB[kp];
+        // this step's partner accumulators: only this lane touches them until the next __syncwarp
+        double2 pa = accA[kp], pb = accB[kp];
+        double pc = accC[kp];
+        // next step's partner (read-only data, prefetched across the barrier)
+        e++;
+        if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
+        const int kpn = ((e & 1) ? Ch : 0) + kc;
+        const double2 Akn = sA[kpn], Bkn = sB[kpn];
         const bool ok1 = t < un.c1, ok2 = (t >= un.t2lo && t < un.c2);
         const double f1 = ok1 ? B1.y : 0.0, f2 = ok2 ? B2.y : 0.0;      // fc_j, zero for idle slots
         const double g1 = ok1 ? Bk.y : 0.0, g2 = ok2 ? Bk.y : 0.0;      // fc_k
@@ -426,28 +435,12 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         s2 = fma(Pb, ctb, s2);
         a2 = fma(Ab_, g2, a2);
         // partner side: ONE shared-memory read-modify-write for both triplets
-        if (phase0) {
-          double2 pa = accA[kp], pb = accB[kp];
-          double pc = accC[kp];
-          pa.x = fma(Pa, A1.x, pa.x); pa.y = fma(Pa, A1.y, pa.y); pb.x = fma(Pa, B1.x, pb.x); pb.y = fma(Pa, cta, pb.y);
-          pa.x = fma(Pb, A2.x, pa.x); pa.y = fma(Pb, A2.y, pa.y); pb.x = fma(Pb, B2.x, pb.x); pb.y = fma(Pb, ctb, pb.y);
-          pc = fma(Aa_, f1, pc); pc = fma(Ab_, f2, pc);
-          accA[kp] = pa; accB[kp] = pb; accC[kp] = pc;
-        }
-        if (straddle) {
-          __syncwarp();
-          if (phase1) {
-            double2 pa = accA[kp], pb = accB[kp];
-            double pc = accC[kp];
-            pa.x = fma(Pa, A1.x, pa.x); pa.y = fma(Pa, A1.y, pa.y); pb.x = fma(Pa, B1.x, pb.x); pb.y = fma(Pa, cta, pb.y);
-            pa.x = fma(Pb, A2.x, pa.x); pa.y = fma(Pb, A2.y, pa.y); pb.x = fma(Pb, B2.x, pb.x); pb.y = fma(Pb, ctb, pb.y);
-            pc = fma(Aa_, f1, pc); pc = fma(Ab_, f2, pc);
-            accA[kp] = pa; accB[kp] = pb; accC[kp] = pc;
-          }
-        }
+        pa.x = fma(Pa, A1.x, pa.x); pa.y = fma(Pa, A1.y, pa.y); pb.x = fma(Pa, B1.x, pb.x); pb.y = fma(Pa, cta, pb.y);
+        pa.x = fma(Pb, A2.x, pa.x); pa.y = fma(Pb, A2.y, pa.y); pb.x = fma(Pb, B2.x, pb.x); pb.y = fma(Pb, ctb, pb.y);
+        pc = fma(Aa_, f1, pc); pc = fma(Ab_, f2, pc);
+        if (un.active) { accA[kp] = pa; accB[kp] = pb; accC[kp] = pc; }
         __syncwarp();
-        e++;
-        if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
+        kp = kpn; Ak = Akn; Bk = Bkn;
       }
       // flush the row side; the same row pair can sit in several lanes (segments) -> one segment at a time
       for (int g = 0; g < sch.Q; g++) {
