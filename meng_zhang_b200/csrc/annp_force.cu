@@ -123,12 +123,11 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
   double *sBias = sW + wtot;
   double *sScale = sBias + btot;
   double *sAvg = sScale + nsf;
-  double *sC2M = sAvg + nsf;                          // [NTSF][NTSF] Chebyshev -> monomial(z) matrix
-  double *blk_end = sC2M + NTSF * NTSF;
+  double *blk_end = sAvg + nsf;
+  const double *__restrict__ gC2M = P.cheb2mono;     // [NTSF][NTSF] Chebyshev -> monomial(z) matrix (L1/L2 resident)
   for (int t = threadIdx.x; t < wtot; t += blockDim.x) sW[t] = P.weights[t];
   for (int t = threadIdx.x; t < btot; t += blockDim.x) sBias[t] = P.bias[t];
   for (int t = threadIdx.x; t < nsf; t += blockDim.x) { sScale[t] = P.sf_scale[t]; sAvg[t] = P.sf_avg[t]; }
-  for (int t = threadIdx.x; t < NTSF * NTSF; t += blockDim.x) sC2M[t] = P.cheb2mono[t];
 
   // ---- per-warp region
   const size_t per_warp_doubles = (size_t) 11 * C + 2 * NTSF + 2 * NPSF + 2 * nsf + (size_t) 2 * nl * nnod + 2 * nnod;
@@ -378,7 +377,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     if (lane < NTSF) {
       double acc = 0.0;
 #pragma unroll
-      for (int n = 0; n < NTSF; n++) acc = fma(sC2M[lane * NTSF + n], sdE[NPSF + n] * sScale[NPSF + n], acc);
+      for (int n = 0; n < NTSF; n++) acc = fma(__ldg(gC2M + lane * NTSF + n), sdE[NPSF + n] * sScale[NPSF + n], acc);
       aK[lane] = acc;
     }
     if (lane < NPSF) {
@@ -523,7 +522,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
 
 size_t annp_force_smem_bytes(const DevParams &hp, int capacity) {
   const int nsf = hp.nsf, nl = hp.nlayers, nnod = hp.nnod;
-  size_t blk = (size_t) (hp.nelements * (hp.w_per_elem + hp.b_per_elem) + 2 * nsf + hp.ntsf * hp.ntsf) * sizeof(double);
+  size_t blk = (size_t) (hp.nelements * (hp.w_per_elem + hp.b_per_elem) + 2 * nsf) * sizeof(double);
   blk = (blk + 15) & ~(size_t) 15;
   size_t per_warp = ((size_t) 11 * capacity + 2 * hp.ntsf + 2 * hp.npsf + 2 * nsf + (size_t) 2 * nl * nnod + 2 * nnod) * sizeof(double) +
                     (size_t) capacity * sizeof(int);
