@@ -1,0 +1,188 @@
+/* ----------------------------------------------------------------------
+   pair_style annp/gpu on libannp_b200.so -- host side inside LAMMPS.
+
+   Mirrors PairANNPGPU of the reference (annp-gpu-lammps/fe_v2/src/pair_annp_gpu.cpp):
+     constructor 61-66, destructor 71-73, memory_usage 76-79, compute 84-131, init_style 136-243.
+   Differences, all on purpose:
+     * the five annp_gpu_* library calls become the C ABI of include/annp_b200.h
+     * forces / energies are ADDED to LAMMPS' arrays (the reference assigns f[][], which breaks
+       pair hybrid/overlay, lal_annp.cpp:336-347)
+     * no `fix gpu` / `package gpu`: the rank picks device (rank mod #devices)
+     * no CPU fallback: a missing device is a fatal error at init_style
+------------------------------------------------------------------------- */
+
+#include "pair_annp_b200.h"
+
+#include "annp_b200.h"
+
+#include "atom.h"
+#include "comm.h"
+#include "error.h"
+#include "force.h"
+#include "memory.h"
+#include "neigh_list.h"
+#include "neigh_request.h"
+#include "neighbor.h"
+#include "suffix.h"
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace LAMMPS_NS;
+
+/* ---------------------------------------------------------------------- */
+
+PairANNPB200::PairANNPB200(LAMMPS *lmp) : PairANNP(lmp), handle(nullptr), nmax_buf(0), fbuf(nullptr), ebuf(nullptr), vbuf(nullptr)
+{
+  respa_enable = 0;
+  suffix_flag |= Suffix::GPU;
+}
+
+/* ---------------------------------------------------------------------- */
+
+PairANNPB200::~PairANNPB200()
+{
+  annp_b200_clear(handle);
+  handle = nullptr;
+  free(fbuf);
+  free(ebuf);
+  free(vbuf);
+}
+
+/* ---------------------------------------------------------------------- */
+
+double PairANNPB200::memory_usage()
+{
+  double bytes = Pair::memory_usage();
+  bytes += (double) nmax_buf * 10 * sizeof(double);
+  return bytes + annp_b200_bytes(handle);
+}
+
+/* ---------------------------------------------------------------------- */
+
+void PairANNPB200::grow_buffers(int nall, int want_e, int want_v)
+{
+  if (nall > nmax_buf) {
+    nmax_buf = nall + nall / 8 + 16;
+    free(fbuf); free(ebuf); free(vbuf);
+    fbuf = (double *) malloc(sizeof(double) * 3 * (size_t) nmax_buf);
+    ebuf = vbuf = nullptr;
+  }
+  if (want_e && !ebuf) ebuf = (double *) malloc(sizeof(double) * (size_t) nmax_buf);
+  if (want_v && !vbuf) vbuf = (double *) malloc(sizeof(double) * 6 * (size_t) nmax_buf);
+  if (!fbuf || (want_e && !ebuf) || (want_v && !vbuf)) error->one(FLERR, "Out of host memory in pair annp/gpu");
+}
+
+/* ----------------------------------------------------------------------
+   compute force and energy   (reference: pair_annp_gpu.cpp:84-131)
+------------------------------------------------------------------------- */
+
+void PairANNPB200::compute(int eflag, int vflag)
+{
+  ev_init(eflag, vflag);
+  const int nlocal = atom->nlocal, nghost = atom->nghost, nall = nlocal + nghost;
+  double **f = atom->f;
+  int rc;
+
+  if (neighbor->ago == 0) {    // reset_nbors of the reference: hand the full list to the device
+    rc = annp_b200_neigh(handle, list->inum, nall, list->ilist, list->numneigh, list->firstneigh);
+    if (rc == ANNP_B200_ENOMEM) error->one(FLERR, "Insufficient memory on accelerator");
+    if (rc) error->one(FLERR, std::string("annp/gpu: ") + annp_b200_last_error(handle));
+  }
+  if (nall == 0) return;
+  grow_buffers(nall, eflag_atom, vflag_atom);
+
+  double eng = 0.0, vir[6] = {0, 0, 0, 0, 0, 0};
+  const int want_pair_virial = vflag_global && !vflag_fdotr;
+  rc = annp_b200_compute(handle, nlocal, nghost, atom->x[0], atom->type, eflag_either, vflag_either || vflag_fdotr,
+                         fbuf, eflag_global ? &eng : nullptr, eflag_atom ? ebuf : nullptr,
+                         want_pair_virial ? vir : nullptr, vflag_atom ? vbuf : nullptr);
+  if (rc == ANNP_B200_ENOMEM) error->one(FLERR, "Insufficient memory on accelerator");
+  if (rc) error->one(FLERR, std::string("annp/gpu: ") + annp_b200_last_error(handle));
+
+  // local and ghost rows: LAMMPS' reverse_comm carries the ghost part home (newton_pair on)
+  double *f0 = f[0];
+  for (int i = 0; i < 3 * nall; i++) f0[i] += fbuf[i];
+  if (eflag_global) eng_vdwl += eng;
+  if (eflag_atom) for (int i = 0; i < nall; i++) eatom[i] += ebuf[i];
+  if (want_pair_virial) for (int k = 0; k < 6; k++) virial[k] += vir[k];
+  if (vflag_atom)
+    for (int i = 0; i < nall; i++) for (int k = 0; k < 6; k++) vatom[i][k] += vbuf[6 * (size_t) i + k];
+
+  if (vflag_fdotr) virial_fdotr_compute();
+}
+
+/* ----------------------------------------------------------------------
+   init specific to this pair style   (reference: pair_annp_gpu.cpp:136-243)
+------------------------------------------------------------------------- */
+
+void PairANNPB200::init_style()
+{
+  if (atom->tag_enable == 0) error->all(FLERR, "Pair style annp/gpu requires atom IDs");
+  if (force->newton_pair == 0) error->all(FLERR, "Pair style annp/gpu requires newton pair on");
+
+  const Param_ANNP &p = params[0];
+  const int ntl = p.ntl, nnod = p.nnod, nsf = p.nsf, nelements = p.nelements, ntypes = atom->ntypes;
+  if (ntl - 1 > ANNP_B200_MAX_LAYERS) error->all(FLERR, "annp/gpu: too many network layers");
+
+  // cutsq exactly as the reference fills it (lines 175-188)
+  for (int i = 1; i <= ntypes; i++)
+    for (int j = i; j <= ntypes; j++) {
+      double cut = 0.0;
+      if (setflag[i][j] != 0 || (setflag[i][i] != 0 && setflag[j][j] != 0)) { cut = init_one(i, j); cut *= cut; }
+      cutsq[i][j] = cutsq[j][i] = cut;
+    }
+
+  // weights/biases flattened row-major per layer, [k + j*ncol] (lines 190-209)
+  const size_t wpe = annp_b200_weights_per_element(ntl, nnod, nsf), bpe = annp_b200_bias_per_element(ntl, nnod);
+  std::vector<double> w(wpe * nelements, 0.0), b(bpe * nelements, 0.0);
+  for (int e = 0; e < nelements; e++) {
+    size_t wo = wpe * e, bo = bpe * e;
+    for (int l = 0; l < ntl - 1; l++) {
+      const int nrow = (l == ntl - 2) ? 1 : nnod, ncol = (l == 0) ? nsf : nnod;
+      for (int j = 0; j < nrow; j++)
+        for (int k = 0; k < ncol; k++) w[wo + k + (size_t) j * ncol] = p.all_annp[e].weight_all[l][j][k];
+      for (int j = 0; j < nrow; j++) b[bo + j] = p.all_annp[e].bias_all[l][0][j];
+      wo += (size_t) nrow * ncol;
+      bo += nrow;
+    }
+  }
+
+  // sfnor_scal = 1/sqrt(cov - avg^2), 0 when degenerate (lines 211-220)
+  std::vector<double> scal(nsf), avg(nsf);
+  for (int i = 0; i < nsf; i++) {
+    avg[i] = p.sfnor_avg[i];
+    const double t = sqrt(p.sfnor_cov[i] - avg[i] * avg[i]);
+    scal[i] = (t <= 1.0e-10) ? 0.0 : 1.0 / t;
+  }
+
+  std::vector<double> cs((size_t) (ntypes + 1) * (ntypes + 1), 0.0);
+  for (int i = 1; i <= ntypes; i++) for (int j = 1; j <= ntypes; j++) cs[(size_t) i * (ntypes + 1) + j] = cutsq[i][j];
+  std::vector<int> mp(ntypes + 1, 0);
+  for (int i = 1; i <= ntypes; i++) mp[i] = map[i] < 0 ? 0 : map[i];
+
+  annp_b200_params P;
+  memset(&P, 0, sizeof(P));
+  P.abi_version = ANNP_B200_ABI_VERSION;
+  P.ntypes = ntypes; P.nelements = nelements;
+  P.ntl = ntl; P.nhl = p.nhl; P.nnod = nnod; P.nsf = nsf; P.npsf = p.npsf; P.ntsf = p.ntsf;
+  P.flagsym = p.flagsym;
+  for (int l = 0; l < ntl - 1; l++) P.flagact[l] = p.flagact[l];
+  P.e_scale = p.e_scale; P.e_shift = p.e_shift; P.e_atom = p.e_atom; P.cut = p.cut;
+  P.sfnor_scal = scal.data(); P.sfnor_avg = avg.data(); P.cutsq = cs.data(); P.map = mp.data();
+  P.weights = w.data(); P.bias = b.data();
+
+  annp_b200_clear(handle);
+  handle = nullptr;
+  const int ndev = annp_b200_device_count();
+  char msg[512] = "";
+  const int device = ndev > 0 ? comm->me % ndev : 0;      // one rank per GPU
+  const int rc = annp_b200_init(&P, device, atom->nlocal + atom->nghost, 0, &handle, msg, (int) sizeof(msg));
+  // the reference funnels init codes through GPU_EXTRA::check_flag, which aborts all ranks (line 235)
+  if (rc == ANNP_B200_ENOMEM) error->all(FLERR, "Insufficient memory on accelerator");
+  if (rc != 0) error->all(FLERR, std::string("annp/gpu initialisation failed: ") + msg);
+
+  neighbor->add_request(this, NeighConst::REQ_FULL);
+}

@@ -17,6 +17,9 @@ BIN = {
     "annp_fe": os.path.join(HERE, "_ref", "ref_annp_fe"),
     "annp_ni": os.path.join(HERE, "_ref", "ref_annp_ni"),
     "anna_adp": os.path.join(HERE, "_ref", "ref_anna_adp"),
+    # NOT an oracle: our own LAMMPS-facing pair style (meng_zhang_b200/lammps/pair_annp_b200.cpp) linked against
+    # libannp_b200.so and driven by the same shim + driver, so it is tested exactly like the reference style
+    "plugin_annp_b200": os.path.join(HERE, "_ref", "plugin_annp_b200"),
 }
 
 

@@ -71,3 +71,17 @@ def test_init_rejects_bad_parameter_blocks(built):
     assert built.annp_b200_init(C.byref(P), -1, 0, 0, C.byref(h), err, 256) == capi.EINVAL
     assert b"Chebyshev" in err.value
     assert built.annp_b200_init(None, -1, 0, 0, C.byref(h), err, 256) == capi.EINVAL
+
+
+def test_lammps_pair_style_binary_fails_loudly_without_gpu(built, fe_pot_file):
+    """meng_zhang_b200/lammps/pair_annp_b200.cpp compiled against the LAMMPS shim (oracle/_ref/plugin_annp_b200):
+    on a box without a GPU init_style must abort with the library's message - there is no CPU path."""
+    from oracle import run_ref
+    import util
+    if built.annp_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    if not run_ref.available("plugin_annp_b200"):
+        pytest.skip("plugin binary not built")
+    cfg, elems, _ = util.load_case("cluster_ragged")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        run_ref.run_reference("plugin_annp_b200", cfg, fe_pot_file, elems)

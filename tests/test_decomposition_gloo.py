@@ -1,0 +1,119 @@
+"""Domain decomposition + halo bookkeeping on CPU (gloo, world_size 2 and 4).
+
+The device kernels (halo_pack / halo_unpack_add / force) need a GPU; here the same send lists, split sizes
+and all_to_all exchanges that meng_zhang_b200/md.py drives over NCCL are exercised with numpy standing in
+for the pack/unpack kernels and the CPU oracle standing in for the force kernel.  Checked:
+  * every rank ends up with exactly the ghost shell LAMMPS would give it
+  * forward + force + reverse reproduces the single-domain forces to rounding (invariance to P)
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import util
+from meng_zhang_b200 import lattice as L
+from meng_zhang_b200.md import build_send_lists, coords_rank, decompose, rank_coords
+
+
+def test_decompose_and_rank_mapping():
+    assert decompose(1) == (1, 1, 1) and decompose(2) == (2, 1, 1) and decompose(4) == (2, 2, 1) and decompose(8) == (2, 2, 2)
+    for n in (1, 2, 4, 8, 6):
+        g = decompose(n)
+        assert g[0] * g[1] * g[2] == n
+        for r in range(n):
+            assert coords_rank(rank_coords(r, g), g) == r
+
+
+def test_send_lists_single_rank_equal_periodic_ghosts():
+    x, box = L.bcc(4, 4, 4)
+    x = L.wrap(L.perturb(x, 0.05, 3), box)
+    idx, shift, counts = build_send_lists(x, np.zeros(3), box, box, (1, 1, 1), (0, 0, 0), 8.5)
+    gx, gowner, _ = L.make_ghosts(x, box, 8.5)
+    mine = np.round(x[idx] + shift, 9)
+    theirs = np.round(gx, 9)
+    assert len(mine) == len(theirs) == counts[0]
+    assert {tuple(r) for r in mine} == {tuple(r) for r in theirs}
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, cells, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import restatement
+        from meng_zhang_b200.pair import read_potential
+        pot = read_potential(util.write_fe_potential(os.path.join(out_dir, f"fe_{rank}.ann")), ["Fe"])
+        grid = decompose(world)
+        x_all, box = L.bcc(*cells)
+        x_all = L.wrap(L.perturb(x_all, 0.05, 21), box)
+        coords = rank_coords(rank, grid)
+        lo = np.array([box[d] * coords[d] / grid[d] for d in range(3)])
+        hi = np.array([box[d] * (coords[d] + 1) / grid[d] for d in range(3)])
+        mine = np.all((x_all >= lo) & (x_all < hi), axis=1)
+        gid = np.nonzero(mine)[0]
+        xl = x_all[mine]
+        nlocal = len(xl)
+        idx, shift, send_counts = build_send_lists(xl, lo, hi, box, grid, coords, 8.5)
+        sc = torch.tensor(send_counts, dtype=torch.int64)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc)
+        recv_counts = [int(c) for c in rc]
+        # forward: pack -> exchange -> ghost block
+        sendbuf = torch.from_numpy(np.ascontiguousarray(xl[idx] + shift))
+        ghosts = torch.empty((sum(recv_counts), 3), dtype=torch.float64)
+        dist.all_to_all_single(ghosts, sendbuf, recv_counts, [int(c) for c in send_counts])
+        x = np.concatenate([xl, ghosts.numpy()])
+        # the ghost shell is exactly the set of periodic images within 8.5 A of the brick
+        gx, _, _ = L.make_ghosts(x_all, box, 8.5 + max(box))     # all images around the box
+        allimg = np.concatenate([x_all, gx])
+        inside = np.all((allimg >= lo - 8.5) & (allimg < hi + 8.5), axis=1) & ~np.all((allimg >= lo) & (allimg < hi), axis=1)
+        assert {tuple(r) for r in np.round(allimg[inside], 8)} == {tuple(r) for r in np.round(ghosts.numpy(), 8)}
+        # force evaluation on the sub-domain (CPU oracle stands in for the kernel)
+        numneigh, neigh = L.full_neighbor_list(x, nlocal, 8.5)
+        cfg = L.Config(nlocal=nlocal, nghost=len(ghosts), x=x, type=np.ones(len(x), dtype=np.int32), ghost_owner=np.zeros(len(ghosts), dtype=np.int32),
+                       ilist=np.arange(nlocal, dtype=np.int32), numneigh=numneigh, neigh=neigh, box=box)
+        o = restatement.compute(pot, cfg)
+        f = o["f"]
+        # reverse: ghost forces -> owners, ordered accumulate
+        back = torch.empty((len(idx), 3), dtype=torch.float64)
+        dist.all_to_all_single(back, torch.from_numpy(np.ascontiguousarray(f[nlocal:])), [int(c) for c in send_counts], recv_counts)
+        floc = f[:nlocal].copy()
+        np.add.at(floc, idx, back.numpy())
+        e = torch.tensor([o["eng_vdwl"]], dtype=torch.float64)
+        dist.all_reduce(e)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), gid=gid, f=floc, e=e.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,cells", [(2, (8, 4, 4)), (4, (8, 8, 4))])
+def test_decomposed_forces_equal_single_domain(world, cells, tmp_path, fe_pot_file):
+    from oracle import restatement
+    from meng_zhang_b200.pair import read_potential
+    mp.spawn(_worker, args=(world, _free_port(), cells, str(tmp_path)), nprocs=world, join=True)
+    x_all, box = L.bcc(*cells)
+    x_all = L.wrap(L.perturb(x_all, 0.05, 21), box)
+    cfg = L.build_config(x_all, box, 6.5)
+    ref = restatement.compute(read_potential(fe_pot_file, ["Fe"]), cfg, nthreads=4)
+    fref = cfg.fold(ref["f"])
+    got = np.zeros_like(fref)
+    seen = np.zeros(len(fref), dtype=int)
+    for r in range(world):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        got[z["gid"]] = z["f"]
+        seen[z["gid"]] += 1
+        assert abs(float(z["e"][0]) - ref["eng_vdwl"]) < 1e-9 * abs(ref["eng_vdwl"])
+    assert np.all(seen == 1)
+    assert np.abs(got - fref).max() < 1e-11

@@ -214,3 +214,21 @@ def test_compute_before_neighbour_list_is_an_error(fe_pot_file):
         pair.compute(1, 0, cfg, ago=5)
     assert ei.value.code == capi.ESTATE
     pair.clear()
+
+
+@pytest.mark.parametrize("name", ["bcc4_perturbed", "cluster_ragged", "bcc4_two_types"])
+def test_lammps_pair_style_through_the_shim_driver(name, fe_pot_file):
+    """The C++ class LAMMPS would compile (PairANNPB200, registered as annp/gpu) run by the same driver that
+    runs the reference's PairANNP: settings -> coeff -> init_style -> compute, LAMMPS flag semantics."""
+    from oracle import run_ref
+    if not run_ref.available("plugin_annp_b200"):
+        pytest.skip("plugin binary not built")
+    cfg, elems, ref = util.load_case(name)
+    for vflag, vkey in ((1 + 4, "virial_pair"), (2, "virial_fdotr")):
+        out = run_ref.run_reference("plugin_annp_b200", cfg, fe_pot_file, elems, eflag=3, vflag=vflag)
+        assert abs(out["eng_vdwl"] - ref["eng_vdwl"]) <= 1e-12 * abs(ref["eng_vdwl"]) + TOL_E
+        assert np.abs(out["eatom"] - ref["eatom"]).max() <= TOL_E
+        assert np.abs(out["f"] - ref["f"]).max() <= TOL_F
+        assert np.abs(out["virial"] - ref[vkey]).max() <= TOL_V
+        if vflag & 4:
+            assert np.abs(out["vatom"] - ref["vatom"]).max() <= TOL_F
