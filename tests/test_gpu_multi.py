@@ -1,0 +1,20 @@
+"""Decomposed device-resident MD over NCCL equals the single-GPU run (needs >= 2 GPUs, else skipped)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_decomposed_md_equals_single_gpu(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + world), os.path.join(ROOT, "scripts", "multi_gpu_check.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "MULTI_GPU_CHECK PASS" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
