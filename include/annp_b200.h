@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ANNP_B200_ABI_VERSION 1
+#define ANNP_B200_ABI_VERSION 2
 
 #define ANNP_B200_MAX_SF 64        /* descriptor components                      */
 #define ANNP_B200_MAX_NOD 32       /* nodes per hidden layer                     */
@@ -61,6 +61,20 @@ typedef struct annp_b200_handle_s *annp_b200_handle;
 
 /* descriptor families: flagsym of the reference (src/pair_annp.cpp:415-417) */
 #define ANNP_B200_SYM_CHEBYSHEV 0
+
+/* Which copy of the reference pair style the numbers are to follow.  The three `annp` copies share the
+ * file format and style name and differ in the source the user installs; the potential file does not say
+ * which one it is for (the Ni file still carries the keyword "Chebyshev"), so the host states it.
+ *   VARIANT_FE  annp-gpu-lammps/fe, fe_v2: Chebyshev radial/angular descriptor, (G - avg)/sigma normalisation,
+ *               E = e_scale*out + e_shift + e_atom, activation 4 = 1.7159 tanh(2x/3) + 0.1 x
+ *   VARIANT_NI  annp-gpu-lammps/ni: Behler-Parrinello G2/G3(narrow) in Bohr (x1.889726), (G - min)/(max - min),
+ *               E = raw network output, forces x51.422515, activations 3 and 4 = tanh
+ *               (ni/src/pair_annp.cpp:74-212, 686-767, 786-807, 858-860) */
+#define ANNP_B200_VARIANT_FE 0
+#define ANNP_B200_VARIANT_NI 1
+/*   VARIANT_ANNA_ADP  anna-gpu-lammps/bcc_fe (`pair_style anna_adp/gpu`): handles of this kind are created by
+ *               anna_b200_init below; every other entry point (neigh, compute, halo, ...) is shared */
+#define ANNP_B200_VARIANT_ANNA_ADP 2
 
 /*
  * Flat parameter block == the argument list of annp_gpu_init (src/pair_annp_gpu.cpp:31-39).
@@ -87,6 +101,13 @@ typedef struct annp_b200_params {
   const int *map;             /* [ntypes+1] */
   const double *weights;      /* see above */
   const double *bias;
+  /* ---- ABI 2 ---- */
+  int variant;                /* ANNP_B200_VARIANT_*                                                     */
+  /* VARIANT_NI only (host_cofsymrad / host_cofsymang of ni/src/pair_annp_gpu.cpp:31-40):
+   *   sym_coerad [npsf][3] = eta, rs (unused by the reference), Rc      sym_coeang [ntsf][4] = eta, lambda, zeta, Rc
+   *   and sfnor_scal = 1/(sf_max - sf_min), sfnor_avg = sf_min */
+  const double *sym_coerad;
+  const double *sym_coeang;
 } annp_b200_params;
 
 /* number of doubles in params.weights / params.bias for one element */
@@ -110,6 +131,11 @@ typedef struct annp_b200_potential {
    * (src/pair_annp.cpp:441-447); bias_all[elem][layer][node].  malloc'd by the reader. */
   double *weight_all;   /* [nelements][ntl-1][nnod][nsf] */
   double *bias_all;     /* [nelements][ntl-1][nnod]      */
+  /* ---- ABI 2: trailing "#coefficent of symmetry funciton" blocks of the Ni files (ni/src/pair_annp.cpp:510-545);
+   * for those files sfnor_cov / sfnor_avg hold the sf_min / sf_max rows */
+  int has_sym_coeff;
+  double sym_coerad[ANNP_B200_MAX_SF][3];
+  double sym_coeang[ANNP_B200_MAX_SF][4];
 } annp_b200_potential;
 
 /* Parse a `.ann` file the way PairANNP::read_file does (line-index addressing, tab-then-digit-or-
@@ -129,6 +155,57 @@ int annp_b200_init(const annp_b200_params *params, int device, int nall_hint, in
 void annp_b200_clear(annp_b200_handle h);
 double annp_b200_bytes(annp_b200_handle h);            /* device bytes currently held */
 const char *annp_b200_last_error(annp_b200_handle h);
+
+/* ---- ANNA-ADP (anna-gpu-lammps/bcc_fe, `pair_style anna_adp/gpu`) ---------------------------------------------
+ *
+ *   anna_b200_read_potential <- PairANNA_ADP::read_file   src/pair_anna_adp.cpp:392-637 (`.anna` file format)
+ *   anna_b200_init           <- anna_adp_gpu_init         src/pair_anna_adp_gpu.cpp:31-40, lib/lal_anna_adp_ext.cpp:25-95
+ *   annp_b200_neigh + annp_b200_compute on the returned handle
+ *                            <- anna_adp_gpu_compute followed by anna_adp_gpu_compute_force
+ *                               (src/pair_anna_adp_gpu.cpp:42-63, 93-157).  The reference GPU style runs with newton
+ *                               off and forward-communicates rho, mu[3], lambda[6], d2, q2 of every atom to the ghosts
+ *                               between its two phases; this library follows the reference CPU style instead
+ *                               (newton on, src/pair_anna_adp.cpp:73-286): everything is centred on the local atom and
+ *                               ghost forces go home through the usual reverse communication, so no per-atom
+ *                               intermediate ever leaves the device.
+ * The numbers follow the CPU style: raw (unnormalised) Chebyshev descriptor -> network (activations 3, 4 =
+ * 1.7 tanh(0.3 x)) -> (d2, q2) -> rho, mu, lambda sums with the smooth step psi -> energy and i-centred forces with
+ * d2, q2 held fixed. */
+#define ANNA_B200_MAX_GPARAMS 32
+typedef struct anna_b200_potential {
+  int nelements;
+  int ntl, nhl, nnod, nout, nsf, npsf, ntsf;
+  int flagsym;
+  int flagact[ANNP_B200_MAX_LAYERS];
+  double cut, e_base, e_scal;
+  int ngp;
+  double gparams[ANNA_B200_MAX_GPARAMS];  /* A0, yy, gamma, C0, c1F, c2F, V0, b1, b2, delta, r0, r1, hc, d1, q1, d3, q3 */
+  int id_elem[ANNP_B200_MAX_ELEMENTS];
+  double mass[ANNP_B200_MAX_ELEMENTS];
+  char elements[ANNP_B200_MAX_ELEMENTS][16];
+  double *weight_all;   /* [nelements][ntl-1][nnod][nsf], rows padded to nsf; last layer has nout rows */
+  double *bias_all;     /* [nelements][ntl-1][nnod] */
+} anna_b200_potential;
+int anna_b200_read_potential(const char *filename, int nelements_coeff, const char *const *elements_coeff,
+                             anna_b200_potential *out, char *err, int errlen);
+void anna_b200_free_potential(anna_b200_potential *pot);
+
+/* Flat parameter block == the argument list of anna_adp_gpu_init.  weights per element: layer 0 [nnod][nsf], hidden
+ * [nnod][nnod], last [nout][nnod], row-major, concatenated; bias likewise (nnod ... nnod, nout). */
+typedef struct anna_b200_params {
+  int abi_version;
+  int ntypes, nelements;
+  int ntl, nhl, nnod, nout, nsf, npsf, ntsf, ngp;
+  int flagsym;
+  int flagact[ANNP_B200_MAX_LAYERS];
+  double e_base, cut;
+  const double *cutsq;        /* [(ntypes+1)*(ntypes+1)] */
+  const int *map;             /* [ntypes+1] */
+  const double *weights;
+  const double *bias;
+  const double *gparams;      /* [ngp], ngp >= 17 */
+} anna_b200_params;
+int anna_b200_init(const anna_b200_params *params, int device, annp_b200_handle *out, char *err, int errlen);
 
 /* ---- LAMMPS host-list mode (gpu_mode == GPU_FORCE) ------------------------------------------ */
 

@@ -14,7 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libannp_b200.so")
 
 MAX_SF, MAX_NOD, MAX_LAYERS, MAX_ELEMENTS, MAX_NEIGH = 64, 32, 6, 4, 384
-ABI_VERSION = 1
+ABI_VERSION = 2
+VARIANT_FE, VARIANT_NI, VARIANT_ANNA_ADP = 0, 1, 2
+MAX_GPARAMS = 32
 
 OK, ENOMEM, ENODEVICE, EINVAL, ECUDA, ESTATE, EOVERFLOW, EIO = 0, -3, -4, -20, -21, -22, -23, -24
 
@@ -31,6 +33,7 @@ class Params(C.Structure):
         ("e_scale", C.c_double), ("e_shift", C.c_double), ("e_atom", C.c_double), ("cut", C.c_double),
         ("sfnor_scal", c_double_p), ("sfnor_avg", c_double_p), ("cutsq", c_double_p), ("map", c_int_p),
         ("weights", c_double_p), ("bias", c_double_p),
+        ("variant", C.c_int), ("sym_coerad", c_double_p), ("sym_coeang", c_double_p),
     ]
 
 
@@ -43,6 +46,28 @@ class Potential(C.Structure):
         ("elements", (C.c_char * 16) * MAX_ELEMENTS),
         ("sfnor_cov", C.c_double * MAX_SF), ("sfnor_avg", C.c_double * MAX_SF),
         ("weight_all", c_double_p), ("bias_all", c_double_p),
+        ("has_sym_coeff", C.c_int), ("sym_coerad", (C.c_double * 3) * MAX_SF), ("sym_coeang", (C.c_double * 4) * MAX_SF),
+    ]
+
+
+class AnnaPotential(C.Structure):
+    _fields_ = [
+        ("nelements", C.c_int), ("ntl", C.c_int), ("nhl", C.c_int), ("nnod", C.c_int), ("nout", C.c_int), ("nsf", C.c_int),
+        ("npsf", C.c_int), ("ntsf", C.c_int), ("flagsym", C.c_int), ("flagact", C.c_int * MAX_LAYERS),
+        ("cut", C.c_double), ("e_base", C.c_double), ("e_scal", C.c_double), ("ngp", C.c_int),
+        ("gparams", C.c_double * MAX_GPARAMS),
+        ("id_elem", C.c_int * MAX_ELEMENTS), ("mass", C.c_double * MAX_ELEMENTS), ("elements", (C.c_char * 16) * MAX_ELEMENTS),
+        ("weight_all", c_double_p), ("bias_all", c_double_p),
+    ]
+
+
+class AnnaParams(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int), ("ntypes", C.c_int), ("nelements", C.c_int),
+        ("ntl", C.c_int), ("nhl", C.c_int), ("nnod", C.c_int), ("nout", C.c_int), ("nsf", C.c_int), ("npsf", C.c_int),
+        ("ntsf", C.c_int), ("ngp", C.c_int), ("flagsym", C.c_int), ("flagact", C.c_int * MAX_LAYERS),
+        ("e_base", C.c_double), ("cut", C.c_double),
+        ("cutsq", c_double_p), ("map", c_int_p), ("weights", c_double_p), ("bias", c_double_p), ("gparams", c_double_p),
     ]
 
 
@@ -62,6 +87,9 @@ PROTOTYPES = {
     "annp_b200_bias_per_element": (C.c_size_t, [C.c_int, C.c_int]),
     "annp_b200_read_potential": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(Potential), C.c_char_p, C.c_int]),
     "annp_b200_free_potential": (None, [C.POINTER(Potential)]),
+    "anna_b200_read_potential": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(AnnaPotential), C.c_char_p, C.c_int]),
+    "anna_b200_free_potential": (None, [C.POINTER(AnnaPotential)]),
+    "anna_b200_init": (C.c_int, [C.POINTER(AnnaParams), C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),
     "annp_b200_init": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),
     "annp_b200_clear": (None, [C.c_void_p]),
     "annp_b200_bytes": (C.c_double, [C.c_void_p]),

@@ -16,6 +16,7 @@
 size_t annp_force_smem_bytes(const DevParams &hp, int capacity);
 bool annp_force_supported(int npsf, int ntsf);
 cudaError_t annp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream, int *blocks_out);
+cudaError_t annp_bp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream);
 void aux_pack_xq(const double *x, const int *type, double4 *xq, int nall, cudaStream_t s);
 void aux_build_reverse(const int *nbr, long long total, int nall, long long *rev_off, int *rev_pos, int *cnt, int *tmp,
                        long long *tile_sum, cudaStream_t s);
@@ -83,7 +84,8 @@ __global__ void k_count_cut(const DevParams *prm, const double4 *__restrict__ xq
       const double4 xj = xq[nbr[p] & ANNP_NEIGHMASK];
       const double dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
       const double rsq = dx * dx + dy * dy + dz * dz;
-      n += !(rsq > prm->cutsq[ti * nt1 + (int) xj.w] || rsq < 1.0e-12);
+      if (prm->variant == ANNP_B200_VARIANT_NI) n += (sqrt(rsq) * 1.889726 < fmax(prm->rad_rc, prm->ang_rc));   // filter of annp_bp_force_kernel
+      else n += !(rsq > prm->cutsq[ti * nt1 + (int) xj.w] || rsq < 1.0e-12);
     }
     for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
     best = max(best, n);
@@ -245,7 +247,8 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
   if (inum > 0) {
     const bool timed = h->timing && h->ev_count < annp_b200_handle_s::kEvRing;
     if (timed) { CK(cudaEventRecord(h->ev0[h->ev_count], s)); }
-    cudaError_t e = annp_force_launch(a, h->hp, h->num_sms, s, nullptr);
+    cudaError_t e = (h->hp.variant == ANNP_B200_VARIANT_NI) ? annp_bp_force_launch(a, h->hp, h->num_sms, s)
+                                                            : annp_force_launch(a, h->hp, h->num_sms, s, nullptr);
     if (e != cudaSuccess) return cuda_fail(h, e, "annp_force_launch");
     if (timed) { CK(cudaEventRecord(h->ev1[h->ev_count], s)); h->ev_count++; }
     h->launches += 1;
@@ -298,26 +301,8 @@ int annp_b200_device_count(void) {
   return n;
 }
 
-int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max_nbors_hint, annp_b200_handle *out,
-                   char *err, int errlen) {
-  (void) nall_hint; (void) max_nbors_hint;
-  if (!p || !out) { set_err(err, errlen, "null argument"); return ANNP_B200_EINVAL; }
-  *out = nullptr;
-  if (p->abi_version != ANNP_B200_ABI_VERSION) { set_err(err, errlen, "ABI version mismatch"); return ANNP_B200_EINVAL; }
-  const int nl = p->ntl - 1;
-  if (p->flagsym != ANNP_B200_SYM_CHEBYSHEV) { set_err(err, errlen, "only the Chebyshev descriptor (flagsym 0) is implemented"); return ANNP_B200_EINVAL; }
-  if (p->ntypes < 1 || p->ntypes > ANNP_MAX_TYPES || p->nelements < 1 || p->nelements > ANNP_B200_MAX_ELEMENTS || nl < 1 ||
-      nl > ANNP_B200_MAX_LAYERS || p->nnod < 1 || p->nnod > ANNP_B200_MAX_NOD || p->nsf != p->npsf + p->ntsf ||
-      p->nsf > ANNP_B200_MAX_SF || p->npsf < 1 || p->ntsf < 1) {
-    set_err(err, errlen, "parameter block outside the supported range");
-    return ANNP_B200_EINVAL;
-  }
-  if (!annp_force_supported(p->npsf, p->ntsf)) {
-    set_err(err, errlen, "no kernel instantiation for this (npsf, ntsf); add it to pick_kernel in annp_force.cu");
-    return ANNP_B200_EINVAL;
-  }
-  if (!p->sfnor_scal || !p->sfnor_avg || !p->cutsq || !p->map || !p->weights || !p->bias) { set_err(err, errlen, "null parameter array"); return ANNP_B200_EINVAL; }
-
+// device checks + handle with stream and event ring (shared by annp_b200_init / anna_b200_init)
+static int open_handle(int device, annp_b200_handle *out, char *err, int errlen) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -330,61 +315,84 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_err(err, errlen, "cannot query device"); return ANNP_B200_ENODEVICE; }
   if (prop.major < 10) { set_err(err, errlen, "device is not sm_100 class; this library is built for sm_100a only"); return ANNP_B200_ENODEVICE; }
   if (cudaSetDevice(device) != cudaSuccess) { set_err(err, errlen, "cudaSetDevice failed"); return ANNP_B200_ENODEVICE; }
-
   annp_b200_handle h = new annp_b200_handle_s();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
-  DevParams &hp = h->hp;
-  memset(&hp, 0, sizeof(hp));
-  hp.ntypes = p->ntypes; hp.nelements = p->nelements; hp.nlayers = nl; hp.nnod = p->nnod;
-  hp.nsf = p->nsf; hp.npsf = p->npsf; hp.ntsf = p->ntsf;
-  for (int l = 0; l < nl; l++) hp.flagact[l] = p->flagact[l];
-  const int nt1 = p->ntypes + 1;
-  for (int t = 0; t < nt1; t++) hp.map[t] = (t == 0) ? 0 : p->map[t];
-  for (int t = 1; t < nt1; t++)
-    if (hp.map[t] < 0 || hp.map[t] >= p->nelements) { delete h; set_err(err, errlen, "type->element map entry out of range"); return ANNP_B200_EINVAL; }
-  for (int a = 0; a < nt1 * nt1; a++) {
-    hp.cutsq[a] = p->cutsq[a];
-    hp.rcinv[a] = p->cutsq[a] > 0.0 ? 1.0 / sqrt(p->cutsq[a]) : 0.0;
+  memset(&h->hp, 0, sizeof(h->hp));
+  memset(&h->last_cnt, 0, sizeof(h->last_cnt));
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    set_err(err, errlen, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    annp_b200_clear(h);
+    return ANNP_B200_ECUDA;
   }
-  hp.cut = p->cut; hp.two_over_cut = 2.0 / p->cut;
-  hp.e_scale = p->e_scale; hp.e_shift = p->e_shift; hp.e_atom = p->e_atom;
-  for (int n = 0; n < p->nsf; n++) { hp.sf_scale[n] = p->sfnor_scal[n]; hp.sf_avg[n] = p->sfnor_avg[n]; }
-  hp.w_per_elem = (int) annp_b200_weights_per_element(p->ntl, p->nnod, p->nsf);
-  hp.b_per_elem = (int) annp_b200_bias_per_element(p->ntl, p->nnod);
-  {
-    int wo = 0, bo = 0;
-    for (int l = 0; l < nl; l++) {
-      hp.w_off[l] = wo; hp.b_off[l] = bo;
-      const int nr = (l == nl - 1) ? 1 : p->nnod, nc = (l == 0) ? p->nsf : p->nnod;
-      wo += nr * nc; bo += nr;
+  for (int k = 0; k < annp_b200_handle_s::kEvRing; k++) {
+    if ((e = cudaEventCreate(&h->ev0[k])) != cudaSuccess || (e = cudaEventCreate(&h->ev1[k])) != cudaSuccess) {
+      set_err(err, errlen, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
+      annp_b200_clear(h);
+      return ANNP_B200_ECUDA;
     }
   }
+  *out = h;
+  return ANNP_B200_OK;
+}
+
+// network shape, type map, cutoffs -> hp; nout = rows of the last layer
+static int fill_network(annp_b200_handle h, int ntypes, int nelements, int ntl, int nnod, int nout, int nsf, int npsf, int ntsf,
+                        const int *flagact, const double *cutsq, const int *map, double cut, char *err, int errlen) {
+  DevParams &hp = h->hp;
+  const int nl = ntl - 1;
+  hp.ntypes = ntypes; hp.nelements = nelements; hp.nlayers = nl; hp.nnod = nnod; hp.nout = nout;
+  hp.nsf = nsf; hp.npsf = npsf; hp.ntsf = ntsf;
+  for (int l = 0; l < nl; l++) hp.flagact[l] = flagact[l];
+  const int nt1 = ntypes + 1;
+  for (int t = 0; t < nt1; t++) hp.map[t] = (t == 0) ? 0 : map[t];
+  for (int t = 1; t < nt1; t++)
+    if (hp.map[t] < 0 || hp.map[t] >= nelements) { set_err(err, errlen, "type->element map entry out of range"); return ANNP_B200_EINVAL; }
+  for (int a = 0; a < nt1 * nt1; a++) {
+    hp.cutsq[a] = cutsq[a];
+    hp.rcinv[a] = cutsq[a] > 0.0 ? 1.0 / sqrt(cutsq[a]) : 0.0;
+  }
+  hp.cut = cut; hp.two_over_cut = 2.0 / cut;
+  int wo = 0, bo = 0;
+  for (int l = 0; l < nl; l++) {
+    hp.w_off[l] = wo; hp.b_off[l] = bo;
+    const int nr = (l == nl - 1) ? nout : nnod, nc = (l == 0) ? nsf : nnod;
+    wo += nr * nc; bo += nr;
+  }
+  hp.w_per_elem = wo; hp.b_per_elem = bo;
+  return ANNP_B200_OK;
+}
+
+static bool valid_shape(int ntypes, int nelements, int ntl, int nnod, int nsf, int npsf, int ntsf) {
+  const int nl = ntl - 1;
+  return !(ntypes < 1 || ntypes > ANNP_MAX_TYPES || nelements < 1 || nelements > ANNP_B200_MAX_ELEMENTS || nl < 1 ||
+           nl > ANNP_B200_MAX_LAYERS || nnod < 1 || nnod > ANNP_B200_MAX_NOD || nsf != npsf + ntsf || nsf > ANNP_B200_MAX_SF ||
+           npsf < 1 || ntsf < 1);
+}
+
+// weights, biases, (Chebyshev variants) the monomial conversion matrix, then the parameter block itself
+static int upload_params(annp_b200_handle h, const double *weights, const double *bias, bool chebyshev, char *err, int errlen) {
+  DevParams &hp = h->hp;
   auto bail = [&](cudaError_t e, const char *w) {
     int rc = cuda_fail(h, e, w);
     set_err(err, errlen, h->err);
-    annp_b200_clear(h);
     return rc;
   };
   cudaError_t e;
-  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
-  for (int k = 0; k < annp_b200_handle_s::kEvRing; k++) {
-    if ((e = cudaEventCreate(&h->ev0[k])) != cudaSuccess) return bail(e, "cudaEventCreate");
-    if ((e = cudaEventCreate(&h->ev1[k])) != cudaSuccess) return bail(e, "cudaEventCreate");
-  }
-  const size_t wbytes = sizeof(double) * (size_t) hp.w_per_elem * p->nelements, bbytes = sizeof(double) * (size_t) hp.b_per_elem * p->nelements;
+  const size_t wbytes = sizeof(double) * (size_t) hp.w_per_elem * hp.nelements, bbytes = sizeof(double) * (size_t) hp.b_per_elem * hp.nelements;
   if ((e = h->d_weights.reserve(wbytes, 1.0)) != cudaSuccess) return bail(e, "cudaMalloc weights");
   if ((e = h->d_bias.reserve(bbytes, 1.0)) != cudaSuccess) return bail(e, "cudaMalloc bias");
   if ((e = h->d_params.reserve(sizeof(DevParams), 1.0)) != cudaSuccess) return bail(e, "cudaMalloc params");
-  if ((e = cudaMemcpy(h->d_weights.p, p->weights, wbytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload weights");
-  if ((e = cudaMemcpy(h->d_bias.p, p->bias, bbytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload bias");
+  if ((e = cudaMemcpy(h->d_weights.p, weights, wbytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload weights");
+  if ((e = cudaMemcpy(h->d_bias.p, bias, bbytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload bias");
   hp.weights = h->d_weights.as<double>();
   hp.bias = h->d_bias.as<double>();
-  {
+  if (chebyshev) {
     // T_n(y) with y = (z+1)/2 written in powers of z = cos(theta): the backward pass evaluates the angular
     // polynomial and its derivative by Horner's rule in z.  All intermediate numbers are dyadic rationals
     // that long double holds exactly for the supported orders.
-    const int nt = p->ntsf;
+    const int nt = hp.ntsf;
     if (nt > 24) return bail(cudaErrorInvalidValue, "ntsf > 24 is not supported by the monomial conversion");
     std::vector<long double> T((size_t) nt * nt, 0.0L), M((size_t) nt * nt, 0.0L);   // T[n][k]: coefficient of y^k
     for (int n = 0; n < nt; n++) {
@@ -410,7 +418,80 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
     hp.cheb2mono = h->d_cheb2mono.as<double>();
   }
   if ((e = cudaMemcpy(h->d_params.p, &hp, sizeof(DevParams), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload params");
-  memset(&h->last_cnt, 0, sizeof(h->last_cnt));
+  return ANNP_B200_OK;
+}
+
+int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max_nbors_hint, annp_b200_handle *out,
+                   char *err, int errlen) {
+  (void) nall_hint; (void) max_nbors_hint;
+  if (!p || !out) { set_err(err, errlen, "null argument"); return ANNP_B200_EINVAL; }
+  *out = nullptr;
+  if (p->abi_version != ANNP_B200_ABI_VERSION) { set_err(err, errlen, "ABI version mismatch"); return ANNP_B200_EINVAL; }
+  const bool ni = p->variant == ANNP_B200_VARIANT_NI;
+  if (p->variant != ANNP_B200_VARIANT_FE && !ni) { set_err(err, errlen, "unknown variant (ANNA-ADP handles are created by anna_b200_init)"); return ANNP_B200_EINVAL; }
+  // the Ni files still say "Chebyshev" on their keyword line; the Ni copy of the style ignores flagsym altogether
+  if (!ni && p->flagsym != ANNP_B200_SYM_CHEBYSHEV) { set_err(err, errlen, "only the Chebyshev descriptor (flagsym 0) is implemented for the Fe copy"); return ANNP_B200_EINVAL; }
+  if (!valid_shape(p->ntypes, p->nelements, p->ntl, p->nnod, p->nsf, p->npsf, p->ntsf)) {
+    set_err(err, errlen, "parameter block outside the supported range");
+    return ANNP_B200_EINVAL;
+  }
+  if (!ni && !annp_force_supported(p->npsf, p->ntsf)) {
+    set_err(err, errlen, "no kernel instantiation for this (npsf, ntsf); add it to pick_kernel in annp_force.cu");
+    return ANNP_B200_EINVAL;
+  }
+  if (!p->sfnor_scal || !p->sfnor_avg || !p->cutsq || !p->map || !p->weights || !p->bias) { set_err(err, errlen, "null parameter array"); return ANNP_B200_EINVAL; }
+  if (ni && (!p->sym_coerad || !p->sym_coeang)) { set_err(err, errlen, "the Ni variant needs sym_coerad / sym_coeang"); return ANNP_B200_EINVAL; }
+
+  annp_b200_handle h = nullptr;
+  int rc = open_handle(device, &h, err, errlen);
+  if (rc) return rc;
+  rc = fill_network(h, p->ntypes, p->nelements, p->ntl, p->nnod, 1, p->nsf, p->npsf, p->ntsf, p->flagact, p->cutsq, p->map, p->cut, err, errlen);
+  if (rc) { annp_b200_clear(h); return rc; }
+  DevParams &hp = h->hp;
+  hp.variant = p->variant;
+  hp.e_scale = p->e_scale; hp.e_shift = p->e_shift; hp.e_atom = p->e_atom;
+  for (int n = 0; n < p->nsf; n++) { hp.sf_scale[n] = p->sfnor_scal[n]; hp.sf_avg[n] = p->sfnor_avg[n]; }
+  if (ni) {
+    for (int m = 0; m < p->npsf; m++) hp.rad_eta[m] = p->sym_coerad[m * 3 + 0];
+    hp.rad_rc = p->sym_coerad[2];                          // Rc of the first row, as the reference (ni/src/pair_annp.cpp:690)
+    for (int n = 0; n < p->ntsf; n++) {
+      hp.ang_eta[n] = p->sym_coeang[n * 4 + 0]; hp.ang_lambda[n] = p->sym_coeang[n * 4 + 1]; hp.ang_zeta[n] = p->sym_coeang[n * 4 + 2];
+    }
+    hp.ang_rc = p->sym_coeang[3];                          // ni/src/pair_annp.cpp:731
+  }
+  rc = upload_params(h, p->weights, p->bias, !ni, err, errlen);
+  if (rc) { annp_b200_clear(h); return rc; }
+  *out = h;
+  return ANNP_B200_OK;
+}
+
+int anna_b200_init(const anna_b200_params *p, int device, annp_b200_handle *out, char *err, int errlen) {
+  if (!p || !out) { set_err(err, errlen, "null argument"); return ANNP_B200_EINVAL; }
+  *out = nullptr;
+  if (p->abi_version != ANNP_B200_ABI_VERSION) { set_err(err, errlen, "ABI version mismatch"); return ANNP_B200_EINVAL; }
+  if (p->flagsym != ANNP_B200_SYM_CHEBYSHEV) { set_err(err, errlen, "only the Chebyshev descriptor (flagsym 0) is implemented"); return ANNP_B200_EINVAL; }
+  if (!valid_shape(p->ntypes, p->nelements, p->ntl, p->nnod, p->nsf, p->npsf, p->ntsf) || p->nout != 2 || p->nout > p->nnod ||
+      p->ngp < 17 || p->ngp > ANNA_B200_MAX_GPARAMS) {
+    set_err(err, errlen, "parameter block outside the supported range (ANNA-ADP needs nout = 2 and >= 17 global parameters)");
+    return ANNP_B200_EINVAL;
+  }
+  if (!annp_force_supported(p->npsf, p->ntsf)) {
+    set_err(err, errlen, "no kernel instantiation for this (npsf, ntsf); add it to pick_kernel in annp_force.cu");
+    return ANNP_B200_EINVAL;
+  }
+  if (!p->cutsq || !p->map || !p->weights || !p->bias || !p->gparams) { set_err(err, errlen, "null parameter array"); return ANNP_B200_EINVAL; }
+  annp_b200_handle h = nullptr;
+  int rc = open_handle(device, &h, err, errlen);
+  if (rc) return rc;
+  rc = fill_network(h, p->ntypes, p->nelements, p->ntl, p->nnod, p->nout, p->nsf, p->npsf, p->ntsf, p->flagact, p->cutsq, p->map, p->cut, err, errlen);
+  if (rc) { annp_b200_clear(h); return rc; }
+  DevParams &hp = h->hp;
+  hp.variant = ANNP_B200_VARIANT_ANNA_ADP;
+  hp.e_base = p->e_base;
+  for (int k = 0; k < 17; k++) hp.gparams[k] = p->gparams[k];
+  for (int n = 0; n < p->nsf; n++) { hp.sf_scale[n] = 1.0; hp.sf_avg[n] = 0.0; }   // raw descriptor (pair_anna_adp.cpp:124-166)
+  rc = upload_params(h, p->weights, p->bias, false, err, errlen);
+  if (rc) { annp_b200_clear(h); return rc; }
   *out = h;
   return ANNP_B200_OK;
 }

@@ -10,6 +10,7 @@
 // Parameter block resident in global memory (one per handle); kernels stage what they need in smem.
 struct DevParams {
   int ntypes, nelements, nlayers /* = ntl-1 */, nnod, nsf, npsf, ntsf;
+  int nout;                                                    // rows of the last layer: 1 (ANNP), 2 (ANNA-ADP: d2, q2)
   int flagact[ANNP_B200_MAX_LAYERS];
   int map[ANNP_MAX_TYPES + 1];
   double cutsq[(ANNP_MAX_TYPES + 1) * (ANNP_MAX_TYPES + 1)];
@@ -25,6 +26,12 @@ struct DevParams {
   const double *bias;
   // [ntsf][ntsf] row-major: monomial coefficient a_k (in z = cos theta) of T_n((z+1)/2) is cheb2mono[k*ntsf+n]
   const double *cheb2mono;
+  // ANNP_B200_VARIANT_NI: Behler-Parrinello coefficients (ni/src/pair_annp.cpp:686-767)
+  int variant;
+  double rad_eta[ANNP_B200_MAX_SF], rad_rc;                    // radial: eta_m, common Rc (Bohr)
+  double ang_eta[ANNP_B200_MAX_SF], ang_lambda[ANNP_B200_MAX_SF], ang_zeta[ANNP_B200_MAX_SF], ang_rc;
+  // ANNP_B200_VARIANT_ANNA_ADP: the 17 global ADP parameters and the energy offset (pair_anna_adp.cpp:97-103)
+  double gparams[17], e_base;
 };
 
 // counters written by the force kernel (one block of 8 x 8 bytes)
@@ -51,6 +58,103 @@ struct ForceArgs {
   int inum;
   int capacity;               // smem neighbour slots per warp
 };
+
+// activation tables of the reference copies: Fe pair_annp.cpp:709-739, Ni ni/src/pair_annp.cpp:786-807,
+// ANNA-ADP pair_anna_adp.cpp:694-718 (3 and 4 = 1.7 tanh(0.3 x); only h is used there)
+__device__ __forceinline__ void annp_activation(int variant, int flag, double z, double &h, double &hd) {
+  const double ca = 1.7159, cb = 0.666666666666667, cc = 0.1;
+  double t;
+  if (variant == ANNP_B200_VARIANT_ANNA_ADP && flag >= 3) {
+    t = tanh(0.3 * z);
+    h = 1.7 * t;
+    hd = 1.7 * 0.3 * (1.0 - t * t);
+    return;
+  }
+  switch (flag) {
+    case 0: h = z; hd = 1.0; break;
+    case 1: h = tanh(z); hd = 1.0 - h * h; break;
+    case 2: h = 1.0 / (1.0 + exp(z)); hd = h * (1.0 - h); break;
+    case 3:
+      if (variant == ANNP_B200_VARIANT_NI) { h = tanh(z); hd = 1.0 - h * h; }
+      else { t = tanh(cb * z); h = ca * t; hd = ca * (1.0 - t * t) * cb; }
+      break;
+    default:
+      if (variant == ANNP_B200_VARIANT_NI) { h = tanh(z); hd = 1.0 - h * h; }
+      else { t = tanh(cb * z); h = ca * t + cc * z; hd = ca * (1.0 - t * t) * cb + cc; }
+      break;
+  }
+}
+
+// Per-atom MLP executed by one warp: forward pass and reverse-mode backprop of the raw output with respect to the
+// (normalised) descriptor.  sG [nsf] in; sdE [nsf] out; returns the raw network output.  sH/sHd: [nl][nnod],
+// sDel: [2][nnod] scratch.  Same maths as the reference's forward-mode Jacobian (pair_annp.cpp:741-804).
+__device__ __forceinline__ double annp_mlp_warp(const DevParams &P, const double *We, const double *Be, const double *sG,
+                                                double *sdE, double *sH, double *sHd, double *sDel, int lane) {
+  const int nsf = P.nsf, nnod = P.nnod, nl = P.nlayers;
+  const double *in = sG;
+  for (int l = 0; l < nl; l++) {
+    const int nr = (l == nl - 1) ? 1 : nnod;
+    const int nc = (l == 0) ? nsf : nnod;
+    const double *W = We + P.w_off[l];
+    if (lane < nr) {
+      double z = 0.0;
+      for (int cidx = 0; cidx < nc; cidx++) z = fma(W[lane * nc + cidx], in[cidx], z);
+      z += Be[P.b_off[l] + lane];
+      double h, hd;
+      annp_activation(P.variant, P.flagact[l], z, h, hd);
+      sH[l * nnod + lane] = h;
+      sHd[l * nnod + lane] = hd;
+    }
+    __syncwarp();
+    in = sH + l * nnod;
+  }
+  const double out = sH[(nl - 1) * nnod];
+  double *dcur = sDel, *dprev = sDel + nnod;        // delta_l[r] = d out / d z_l[r]
+  if (lane == 0) dcur[0] = sHd[(nl - 1) * nnod];
+  __syncwarp();
+  for (int l = nl - 1; l >= 1; l--) {
+    const int nr = (l == nl - 1) ? 1 : nnod;
+    const double *W = We + P.w_off[l];               // [nr][nnod]
+    if (lane < nnod) {
+      double s = 0.0;
+      for (int r = 0; r < nr; r++) s = fma(W[r * nnod + lane], dcur[r], s);
+      dprev[lane] = s * sHd[(l - 1) * nnod + lane];
+    }
+    __syncwarp();
+    double *tmp = dcur; dcur = dprev; dprev = tmp;
+  }
+  const int nr0 = (nl == 1) ? 1 : nnod;
+  const double *W0 = We + P.w_off[0];                // [nr0][nsf]
+  for (int n = lane; n < nsf; n += 32) {
+    double s = 0.0;
+    for (int r = 0; r < nr0; r++) s = fma(W0[r * nsf + n], dcur[r], s);
+    sdE[n] = s;
+  }
+  __syncwarp();
+  return out;
+}
+
+// Forward pass only (ANNA-ADP, pair_anna_adp.cpp:720-751): the nout outputs are left in sH[(nl-1)*nnod + k].
+__device__ __forceinline__ void annp_mlp_forward_warp(const DevParams &P, const double *We, const double *Be, const double *sG,
+                                                      double *sH, int lane) {
+  const int nsf = P.nsf, nnod = P.nnod, nl = P.nlayers;
+  const double *in = sG;
+  for (int l = 0; l < nl; l++) {
+    const int nr = (l == nl - 1) ? P.nout : nnod;
+    const int nc = (l == 0) ? nsf : nnod;
+    const double *W = We + P.w_off[l];
+    if (lane < nr) {
+      double z = 0.0;
+      for (int cidx = 0; cidx < nc; cidx++) z = fma(W[lane * nc + cidx], in[cidx], z);
+      z += Be[P.b_off[l] + lane];
+      double h, hd;
+      annp_activation(P.variant, P.flagact[l], z, h, hd);
+      sH[l * nnod + lane] = h;
+    }
+    __syncwarp();
+    in = sH + l * nnod;
+  }
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

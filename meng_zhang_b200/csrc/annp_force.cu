@@ -96,20 +96,114 @@ __device__ __forceinline__ Unit make_unit(const Sched &sc, int pass, int lane) {
   return u;
 }
 
-__device__ __forceinline__ void activation(int flag, double z, double &h, double &hd) {
-  // reference table: pair_annp.cpp:709-739 (Fe copy)
-  const double ca = 1.7159, cb = 0.666666666666667, cc = 0.1;
-  double t;
-  switch (flag) {
-    case 0: h = z; hd = 1.0; break;
-    case 1: h = tanh(z); hd = 1.0 - h * h; break;
-    case 2: h = 1.0 / (1.0 + exp(z)); hd = h * (1.0 - h); break;
-    case 3: t = tanh(cb * z); h = ca * t; hd = ca * (1.0 - t * t) * cb; break;
-    default: t = tanh(cb * z); h = ca * t + cc * z; hd = ca * (1.0 - t * t) * cb + cc; break;
+// ANNA-ADP tail (MODE 1): the descriptor of the centre atom is in sG (raw sums).  Reference: pair_anna_adp.cpp:166-272.
+//   network -> (d2, q2); per-neighbour sums rho, mu[3], lambda[3][3], E_rep with the smooth step psi = z^4/(1+z^4),
+//   z = (r - Rc)/hc; E_i; then the i-centred pair forces with d2, q2 held fixed, written at the neighbours' list
+//   positions like the ANNP forces.  One lane per neighbour, fixed butterfly sums -> deterministic.
+__device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParams &P, const double *We, const double *Be,
+                                              const double *sG, double *sH, const double2 *sA, const double2 *sB,
+                                              const double2 *sC, const int *spos, int N, int Ch, long long p0, int ii, int lane) {
+#define ROWPOS(r) ((((r) & 1) ? Ch : 0) + ((r) >> 1))
+  annp_mlp_forward_warp(P, We, Be, sG, sH, lane);
+  const double d2 = sH[(P.nlayers - 1) * P.nnod], q2 = sH[(P.nlayers - 1) * P.nnod + 1];
+  if (a.G_dbg)
+    for (int n = lane; n < P.nsf; n += 32) { a.G_dbg[(size_t) ii * P.nsf + n] = sG[n]; a.dEdG_dbg[(size_t) ii * P.nsf + n] = (n == 0) ? d2 : (n == 1 ? q2 : 0.0); }
+  const double *gp = P.gparams;
+  const double A0 = gp[0], yy = gp[1], gamma = gp[2], C0 = gp[3], c1F = gp[4], c2F = gp[5], V0 = gp[6], b1 = gp[7];
+  const double b2 = gp[8], delta = gp[9], r0 = gp[10], r1 = gp[11], hc = gp[12], d1 = gp[13], q1 = gp[14], d3 = gp[15], q3 = gp[16];
+  const double Rc = P.cut, hcinv = 1.0 / hc;
+  const double rep_coeff = V0 / (b2 - b1);
+  double rho = 0, mx = 0, my = 0, mz = 0, lxx = 0, lyy = 0, lzz = 0, lxy = 0, lxz = 0, lyz = 0, erep = 0;
+  for (int s = lane; s < N; s += 32) {
+    const int ps = ROWPOS(s);
+    const double2 A = sA[ps], B = sB[ps], Cc = sC[ps];
+    const double r = Cc.y;
+    if (r > Rc) continue;                                          // pair_anna_adp.cpp:178 (r >= 1e-6 by the filter)
+    const double x = r * A.x, y = r * A.y, z = r * B.x;
+    const double sx = (r - Rc) * hcinv, sx2 = sx * sx, sx4 = sx2 * sx2;
+    const double stp = sx4 / (1.0 + sx4);
+    const double u = stp * (d1 * exp(-d2 * r) + d3);
+    const double w = stp * (q1 * exp(-q2 * r) + q3);
+    mx = fma(u, x, mx); my = fma(u, y, my); mz = fma(u, z, mz);
+    lxx = fma(w * x, x, lxx); lyy = fma(w * y, y, lyy); lzz = fma(w * z, z, lzz);
+    lxy = fma(w * x, y, lxy); lxz = fma(w * x, z, lxz); lyz = fma(w * y, z, lyz);
+    const double rz = r - r0, ez = exp(-gamma * rz);
+    rho += stp * (A0 * pow(rz, yy) * ez * (1.0 + ez) + C0);
+    const double pz = r / r1;
+    erep += stp * (rep_coeff * (b2 / pow(pz, b1) - b1 / pow(pz, b2)) + delta);
   }
+  rho = warp_sum(rho); mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
+  lxx = warp_sum(lxx); lyy = warp_sum(lyy); lzz = warp_sum(lzz);
+  lxy = warp_sum(lxy); lxz = warp_sum(lxz); lyz = warp_sum(lyz); erep = warp_sum(erep);
+  const double v_i = lxx + lyy + lzz;
+  const double sum_mu = mx * mx + my * my + mz * mz;
+  const double sum_lam = lxx * lxx + lyy * lyy + lzz * lzz + 2.0 * (lxy * lxy + lxz * lxz + lyz * lyz);
+  const double f_v = -1.0 / 3.0 * v_i;
+  const double e_ang = 0.5 * sum_mu + 0.5 * sum_lam - 1.0 / 6.0 * v_i * v_i;
+  const double e_emb = c1F * sqrt(rho) + c2F * rho * rho;
+  const double e_i = 0.5 * erep + e_emb + e_ang + P.e_base;           // pair_anna_adp.cpp:213
+  const double demb = 0.5 * c1F / sqrt(rho) + 2.0 * c2F * rho;
+
+  double fix = 0, fiy = 0, fiz = 0;
+  double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
+  for (int s = lane; s < N; s += 32) {
+    const int ps = ROWPOS(s);
+    const double2 A = sA[ps], B = sB[ps], Cc = sC[ps];
+    const double r = Cc.y;
+    const int q = spos[s];
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    const double x = r * A.x, y = r * A.y, z = r * B.x;
+    if (!(r > Rc)) {
+      const double sx = (r - Rc) * hcinv, sx2 = sx * sx, sx4 = sx2 * sx2;
+      const double t1 = 1.0 + sx4;
+      const double stp = sx4 / t1;
+      const double dstp = 4.0 * sx2 * sx / (t1 * t1) * hcinv;
+      const double rz = r - r0, ez = exp(-gamma * rz);
+      const double zyy = A0 * pow(rz, yy), gz = zyy * gamma;
+      const double drho = ez * (1.0 + ez) * (zyy * (dstp + stp * yy / rz) - gz) + C0 * dstp - gz * ez * ez;
+      const double d_emb = demb * drho;
+      const double pz = r / r1, zb1 = pow(pz, b1), zb2 = pow(pz, b2);
+      const double rep_t1 = rep_coeff * (b2 / zb1 - b1 / zb2) + delta;
+      const double d_rep = dstp * rep_t1 + stp * rep_coeff * ((b2 * b1 / r1) / pz * (-1.0 / zb1 + 1.0 / zb2));
+      const double ut = d1 * exp(-d2 * r), wt = q1 * exp(-q2 * r);
+      const double au = stp * (ut + d3), aw = 2.0 * stp * (wt + q3);
+      const double dau = dstp * (ut + d3) + stp * (-d2 * ut);
+      const double daw = dstp * (wt + q3) + stp * (-q2 * wt);
+      const double dl1 = daw * (lxx * x * x + lyy * y * y + lzz * z * z);
+      const double dl2 = daw * (lxy * x * y + lxz * x * z + lyz * y * z) * 2.0 + dl1;
+      const double df1 = 0.5 * d_rep + d_emb + dau * (mx * x + my * y + mz * z) + dl2;
+      const double df3 = f_v * (daw * r + aw);
+      const double rinv = 1.0 / r;
+      fx = df1 * x * rinv + aw * (y * lxy + z * lxz + x * lxx) + mx * au + x * df3;
+      fy = df1 * y * rinv + aw * (y * lyy + z * lyz + x * lxy) + my * au + y * df3;
+      fz = df1 * z * rinv + aw * (y * lyz + z * lzz + x * lxz) + mz * au + z * df3;
+    }
+    a.fpair[p0 + q] = make_double4(fx, fy, fz, 0.0);                  // f[j] += (fx, fy, fz), f[i] -=
+    fix -= fx; fiy -= fy; fiz -= fz;
+    if (a.vir_c || a.vpair) {                                         // ev_tally_xyz(i, j, .., -f, x_ij)
+      const double w0 = -x * fx, w1 = -y * fy, w2 = -z * fz, w3 = -x * fy, w4 = -x * fz, w5 = -y * fz;
+      v0 += w0; v1 += w1; v2 += w2; v3 += w3; v4 += w4; v5 += w5;
+      if (a.vpair) {
+        double *vp = a.vpair + (size_t) (p0 + q) * 6;
+        vp[0] = w0; vp[1] = w1; vp[2] = w2; vp[3] = w3; vp[4] = w4; vp[5] = w5;
+      }
+    }
+  }
+  fix = warp_sum(fix); fiy = warp_sum(fiy); fiz = warp_sum(fiz);
+  if (lane == 0) a.fself[ii] = make_double4(fix, fiy, fiz, e_i);
+  if (a.vir_c) {
+    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
+    v3 = warp_sum(v3); v4 = warp_sum(v4); v5 = warp_sum(v5);
+    if (lane == 0) {
+      double *vc = a.vir_c + (size_t) ii * 6;
+      vc[0] = v0; vc[1] = v1; vc[2] = v2; vc[3] = v3; vc[4] = v4; vc[5] = v5;
+    }
+  }
+  __syncwarp();
+#undef ROWPOS
 }
 
-template <int NPSF, int NTSF>
+template <int NPSF, int NTSF, int MODE>
 __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -317,56 +411,17 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     }
     __syncwarp();
 
-    // ------------------------------------------------------------------ 3. MLP forward + backprop
     const int elem = P.map[ti];
     const double *We = sW + elem * P.w_per_elem;
     const double *Be = sBias + elem * P.b_per_elem;
-    {
-      const double *in = sG;
-      for (int l = 0; l < nl; l++) {
-        const int nr = (l == nl - 1) ? 1 : nnod;
-        const int nc = (l == 0) ? nsf : nnod;
-        const double *W = We + P.w_off[l];
-        if (lane < nr) {
-          double z = 0.0;
-          for (int cidx = 0; cidx < nc; cidx++) z = fma(W[lane * nc + cidx], in[cidx], z);
-          z += Be[P.b_off[l] + lane];
-          double h, hd;
-          activation(P.flagact[l], z, h, hd);
-          sH[l * nnod + lane] = h;
-          sHd[l * nnod + lane] = hd;
-        }
-        __syncwarp();
-        in = sH + l * nnod;
-      }
+    if constexpr (MODE == 1) {      // ANNA-ADP: forward network + ADP energy and forces, no descriptor derivatives
+      anna_adp_tail(a, P, We, Be, sG, sH, sA, sB, sC, spos, N, Ch, p0, ii, lane);
+      continue;
     }
-    const double out = sH[(nl - 1) * nnod];
+
+    // ------------------------------------------------------------------ 3. MLP forward + backprop
+    const double out = annp_mlp_warp(P, We, Be, sG, sdE, sH, sHd, sDel, lane);
     const double e_i = P.e_scale * out + P.e_shift + P.e_atom;      // pair_annp.cpp:790-793
-    {
-      // delta_l[r] = d out / d z_l[r]
-      double *dcur = sDel, *dprev = sDel + nnod;
-      if (lane == 0) dcur[0] = sHd[(nl - 1) * nnod];
-      __syncwarp();
-      for (int l = nl - 1; l >= 1; l--) {
-        const int nr = (l == nl - 1) ? 1 : nnod;
-        const double *W = We + P.w_off[l];           // [nr][nnod]
-        if (lane < nnod) {
-          double s = 0.0;
-          for (int r = 0; r < nr; r++) s = fma(W[r * nnod + lane], dcur[r], s);
-          dprev[lane] = s * sHd[(l - 1) * nnod + lane];
-        }
-        __syncwarp();
-        double *tmp = dcur; dcur = dprev; dprev = tmp;
-      }
-      const int nr0 = (nl == 1) ? 1 : nnod;
-      const double *W0 = We + P.w_off[0];            // [nr0][nsf]
-      for (int n = lane; n < nsf; n += 32) {
-        double s = 0.0;
-        for (int r = 0; r < nr0; r++) s = fma(W0[r * nsf + n], dcur[r], s);
-        sdE[n] = s;
-      }
-      __syncwarp();
-    }
     if (a.G_dbg) for (int n = lane; n < nsf; n += 32) { a.G_dbg[(size_t) ii * nsf + n] = sG[n]; a.dEdG_dbg[(size_t) ii * nsf + n] = sdE[n]; }
 
     // Chebyshev-T coefficients c_n = s_n dOut/dG_n  ->  U-basis coefficients
@@ -532,10 +587,15 @@ size_t annp_force_smem_bytes(const DevParams &hp, int capacity) {
 
 typedef void (*force_kernel_t)(const ForceArgs);
 
-static force_kernel_t pick_kernel(int npsf, int ntsf) {
-  if (npsf == 9 && ntsf == 19) return annp_force_kernel<9, 19>;     // fe / fe_v2 potential
-  if (npsf == 8 && ntsf == 20) return annp_force_kernel<8, 20>;
-  if (npsf == 4 && ntsf == 6) return annp_force_kernel<4, 6>;       // small set used by unit tests
+static force_kernel_t pick_kernel(int npsf, int ntsf, int variant = ANNP_B200_VARIANT_FE) {
+  if (variant == ANNP_B200_VARIANT_ANNA_ADP) {
+    if (npsf == 9 && ntsf == 19) return annp_force_kernel<9, 19, 1>;  // fe_adp_potential_2310.anna
+    if (npsf == 4 && ntsf == 6) return annp_force_kernel<4, 6, 1>;
+    return nullptr;
+  }
+  if (npsf == 9 && ntsf == 19) return annp_force_kernel<9, 19, 0>;     // fe / fe_v2 potential
+  if (npsf == 8 && ntsf == 20) return annp_force_kernel<8, 20, 0>;
+  if (npsf == 4 && ntsf == 6) return annp_force_kernel<4, 6, 0>;       // small set used by unit tests
   return nullptr;
 }
 
@@ -544,7 +604,7 @@ bool annp_force_supported(int npsf, int ntsf) { return pick_kernel(npsf, ntsf) !
 // Launch on `stream`. grid_blocks <= 0 picks one full wave of resident blocks.
 cudaError_t annp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream,
                               int *blocks_out) {
-  force_kernel_t k = pick_kernel(hp.npsf, hp.ntsf);
+  force_kernel_t k = pick_kernel(hp.npsf, hp.ntsf, hp.variant);
   if (!k) return cudaErrorInvalidValue;
   const size_t smem = annp_force_smem_bytes(hp, args.capacity);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);

@@ -46,6 +46,14 @@ class AnnPotential:
     sfnor_avg: np.ndarray      # [nsf]
     weight_all: np.ndarray     # [nelements][ntl-1][nnod][nsf]  rows padded with zeros
     bias_all: np.ndarray       # [nelements][ntl-1][nnod]
+    # Ni copy only (ni/src/pair_annp.cpp:510-545): sfnor_cov / sfnor_avg then hold the sf_min / sf_max rows
+    sym_coerad: np.ndarray | None = None   # [npsf][3] eta, rs, Rc
+    sym_coeang: np.ndarray | None = None   # [ntsf][4] eta, lambda, zeta, Rc
+
+    @property
+    def variant(self) -> int:
+        """The file itself does not name the copy it is for; only Ni files carry the coefficient blocks."""
+        return capi.VARIANT_NI if self.sym_coerad is not None else capi.VARIANT_FE
 
     def sf_scale(self) -> np.ndarray:
         """s_n = 1/sqrt(cov - avg^2), 0 if <= 1e-10 (pair_annp.cpp:98-108, pair_annp_gpu.cpp:211-220)."""
@@ -89,7 +97,9 @@ def read_potential(filename: str, elements_coeff=("Fe",)) -> AnnPotential:
             id_elem=[pot.id_elem[i] for i in range(pot.nelements)], mass=[pot.mass[i] for i in range(pot.nelements)],
             elements=[pot.elements[i].value.decode() for i in range(pot.nelements)],
             sfnor_cov=np.array(pot.sfnor_cov[:pot.nsf]), sfnor_avg=np.array(pot.sfnor_avg[:pot.nsf]),
-            weight_all=w, bias_all=b)
+            weight_all=w, bias_all=b,
+            sym_coerad=np.array([list(pot.sym_coerad[i]) for i in range(pot.npsf)]) if pot.has_sym_coeff else None,
+            sym_coeang=np.array([list(pot.sym_coeang[i]) for i in range(pot.ntsf)]) if pot.has_sym_coeff else None)
     finally:
         L.annp_b200_free_potential(C.byref(pot))
 
@@ -100,13 +110,14 @@ def write_potential(path: str, pot: AnnPotential, comment: str = "written by men
     act_names = {0: "linear", 1: "hyp", 2: "sig", 3: "mod", 4: "tanh"}   # only the scanned 2-char keys
     sym = {0: "Chebyshev", 1: "Behler", 2: "Customized"}[pot.flagsym]
     fmt = lambda v: repr(float(v))
+    ni = pot.sym_coerad is not None
     lines = [f"#Sourse: {comment}", "#Date: -", "#contact information: -", "",
              "#element parameters_(nelement #n element mass)", str(pot.nelements)]
     for e in range(pot.nelements):
         lines.append(f"{pot.id_elem[e]}\t{pot.elements[e]}\t{fmt(pot.mass[e])}")
     lines += ["", "#artificial neural network parameters_(TL HL Nodes_HL Num_SF Num_PSF Num_TSF Cut) ",
               f"{pot.ntl}\t{pot.nhl}\t{pot.nnod}\t{pot.nsf}\t{pot.npsf}\t{pot.ntsf}\t{fmt(pot.cut)} ", "",
-              "#symmetry function normization_(sfval_cov sfval_avg)",
+              "#symmetry function normization_(sf_min sf_max)" if ni else "#symmetry function normization_(sfval_cov sfval_avg)",
               "\t".join(fmt(v) for v in pot.sfnor_cov), "\t".join(fmt(v) for v in pot.sfnor_avg), "",
               "#types of symmetry function and activation function",
               "\t".join([sym] + [act_names[a] for a in pot.flagact]), "",
@@ -123,6 +134,14 @@ def write_potential(path: str, pot: AnnPotential, comment: str = "written by men
             lines.append(f"#{l + 1}_(bias)")
             lines.append("\t".join(fmt(v) for v in pot.bias_all[e, l, :nrow]))
             lines.append("")
+    if ni:
+        # trailing blocks of the Ni files; values are only picked up after TAB + digit/'-', the element names are not
+        lines += ["#coefficent of symmetry funciton", f"#rad\t{pot.npsf}"]
+        for row in pot.sym_coerad:
+            lines.append(pot.elements[0] + "\t" + "\t".join(fmt(v) for v in row))
+        lines.append(f"#angl\t{pot.ntsf}")
+        for row in pot.sym_coeang:
+            lines.append(pot.elements[0] + "\t" + pot.elements[0] + "\t" + "\t".join(fmt(v) for v in row))
     with open(path, "w", newline="") as fp:
         fp.write("\r\n".join(lines) + "\r\n")
 
@@ -147,7 +166,10 @@ class PairANNPGPU:
     After compute: pair.eng_vdwl, pair.eatom, pair.virial (6), pair.vatom as in LAMMPS' Pair.
     """
 
-    def __init__(self, ntypes: int = 1, device: int = -1, newton_pair: int = 1, skin: float = 2.0):
+    def __init__(self, ntypes: int = 1, device: int = -1, newton_pair: int = 1, skin: float = 2.0, variant: int | None = None):
+        """variant: which copy of the reference style to follow (capi.VARIANT_FE / VARIANT_NI); None = decide from the
+        potential file (Ni files carry symmetry-function coefficient blocks, Fe files do not)."""
+        self.variant = variant
         self.ntypes = ntypes
         self.device = device
         self.newton_pair = newton_pair
@@ -230,8 +252,19 @@ class PairANNPGPU:
                 else:
                     self.cutsq[i, j] = self.cutsq[j, i] = 0.0
         w, b = p.flat_weights()
-        scal = np.ascontiguousarray(p.sf_scale())
-        avg = np.ascontiguousarray(p.sfnor_avg, dtype=np.float64)
+        variant = p.variant if self.variant is None else self.variant
+        if variant == capi.VARIANT_NI:
+            if p.sym_coerad is None:
+                raise LammpsError("potential file has no symmetry-function coefficient blocks (needed by the Ni copy)")
+            # (G - sf_min) / (sf_max - sf_min), ni/src/pair_annp.cpp:99-101,168-170
+            scal = np.ascontiguousarray(1.0 / (p.sfnor_avg - p.sfnor_cov))
+            avg = np.ascontiguousarray(p.sfnor_cov, dtype=np.float64)
+            corad = np.ascontiguousarray(p.sym_coerad, dtype=np.float64)
+            coang = np.ascontiguousarray(p.sym_coeang, dtype=np.float64)
+        else:
+            scal = np.ascontiguousarray(p.sf_scale())
+            avg = np.ascontiguousarray(p.sfnor_avg, dtype=np.float64)
+            corad = coang = None
         cutsq = np.ascontiguousarray(self.cutsq.reshape(-1))
         mp = np.ascontiguousarray(np.where(self.map < 0, 0, self.map).astype(np.int32))
         P = capi.Params()
@@ -244,6 +277,9 @@ class PairANNPGPU:
         P.e_scale, P.e_shift, P.e_atom, P.cut = p.e_scale, p.e_shift, p.e_atom, p.cut
         P.sfnor_scal, P.sfnor_avg, P.cutsq, P.map = _dp(scal), _dp(avg), _dp(cutsq), _ip(mp)
         P.weights, P.bias = _dp(w), _dp(b)
+        P.variant = variant
+        if corad is not None:
+            P.sym_coerad, P.sym_coeang = _dp(corad), _dp(coang)
         self.clear()
         err = C.create_string_buffer(512)
         h = C.c_void_p(None)

@@ -24,27 +24,7 @@
 #include <omp.h>
 #endif
 
-#define ORACLE_MAX_SF 64
-#define ORACLE_MAX_NOD 64
-#define ORACLE_MAX_LAYERS 8
-#define NEIGHMASK 0x1FFFFFFF
-#define MY_PI 3.14159265358979323846
-
-typedef struct {
-  int ntypes;               /* LAMMPS atom types, 1-based                              */
-  int nelements;            /* elements in the potential file                          */
-  int ntl, nhl, nnod;       /* total layers (incl. input), hidden layers, nodes/layer  */
-  int nsf, npsf, ntsf;      /* descriptor sizes: total, radial, angular                */
-  int flagsym;              /* 0 = Chebyshev                                           */
-  int flagact[ORACLE_MAX_LAYERS];
-  double cut, e_scale, e_shift, e_atom;
-  const double *sfnor_cov;  /* [nsf]                                                   */
-  const double *sfnor_avg;  /* [nsf]                                                   */
-  const int *map;           /* [ntypes+1] type -> element                              */
-  const double *cutsq;      /* [(ntypes+1)*(ntypes+1)]                                 */
-  const double *weights;    /* [nelements][ntl-1][nnod][nsf]  (weight_all, padded)     */
-  const double *bias;       /* [nelements][ntl-1][nnod]       (bias_all[..][0][..])    */
-} oracle_params_t;
+#include "oracle_params.h"
 
 /* pair_annp.cpp:590-594 */
 static void annp_fc(double rij, double Rc, double *fc, double *dfc) {

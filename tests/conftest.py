@@ -27,3 +27,15 @@ def built():
 def fe_pot_file(tmp_path_factory, built):
     import util
     return util.write_fe_potential(tmp_path_factory.mktemp("pot") / "fe_annp_potential.ann")
+
+
+@pytest.fixture(scope="session")
+def ni_pot_file(tmp_path_factory, built):
+    import util
+    return util.write_ni_potential(tmp_path_factory.mktemp("pot") / "ni_annp_potential.ann")
+
+
+@pytest.fixture(scope="session")
+def anna_pot_file(tmp_path_factory, built):
+    import util
+    return util.write_anna_fe_potential(tmp_path_factory.mktemp("pot") / "fe_adp_potential.anna")

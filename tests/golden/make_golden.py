@@ -8,6 +8,8 @@ Needs /root/reference and the binaries of `make -C oracle` (oracle/_ref/ref_*). 
                                    suite re-creates a `.ann` file from it with pair.write_potential)
   tests/golden/annp_fe_*.npz       inputs (x, type, ghosts, neighbour rows) and the reference's outputs
                                    (eng_vdwl, eatom, f, virial by pair tally and by f.r, vatom)
+  tests/golden/ni_potential.json, anna_potential.json, annp_ni_*.npz, anna_adp_*.npz
+                                   the same for the Ni copy of the style (ref_annp_ni) and for ANNA-ADP (ref_anna_adp)
   tests/golden/fe_st.npz           the 152 880-atom slab of `performance test.zip` + its logged thermo values
 The GPU box has no /root/reference: tests read only these files.
 """
@@ -114,7 +116,93 @@ def dump_fe_st():
     print("fe_st:", natoms, box.tolist())
 
 
+NI_POT = f"{REF}/annp-gpu-lammps/ni/ni_annp_potential_2.ann"
+ANNA_POT = f"{REF}/anna-gpu-lammps/bcc_fe/fe_adp_potential_2310.anna"
+
+
+def dump_ni_anna_potentials():
+    """Parsed numbers of the Ni `.ann` and the ANNA-ADP `.anna` file (tests re-create the files with the writers)."""
+    from meng_zhang_b200.pair_anna import read_anna_potential
+    pot = read_potential(NI_POT, ["Ni"])
+    d = {k: getattr(pot, k) for k in ("nelements", "ntl", "nhl", "nnod", "nsf", "npsf", "ntsf", "flagsym", "flagact",
+                                      "cut", "e_scale", "e_shift", "e_atom", "id_elem", "mass", "elements")}
+    for k in ("sfnor_cov", "sfnor_avg", "weight_all", "bias_all", "sym_coerad", "sym_coeang"):
+        d[k] = getattr(pot, k).tolist()
+    d["source"] = "annp-gpu-lammps/ni/ni_annp_potential_2.ann (MPL-2.0), parsed numbers only"
+    with open(os.path.join(OUT, "ni_potential.json"), "w") as fp:
+        json.dump(d, fp)
+    pa = read_anna_potential(ANNA_POT, ["Fe"])
+    d = {k: getattr(pa, k) for k in ("nelements", "ntl", "nhl", "nnod", "nout", "nsf", "npsf", "ntsf", "flagsym", "flagact",
+                                     "cut", "e_base", "e_scal", "ngp", "id_elem", "mass", "elements")}
+    for k in ("gparams", "weight_all", "bias_all"):
+        d[k] = getattr(pa, k).tolist()
+    d["source"] = "anna-gpu-lammps/bcc_fe/fe_adp_potential_2310.anna (MPL-2.0), parsed numbers only"
+    with open(os.path.join(OUT, "anna_potential.json"), "w") as fp:
+        json.dump(d, fp)
+
+
+def ni_cases():
+    """Ni copy: thermally perturbed cells only - in a perfect lattice 1 + lambda cos(theta) = 0 sits on the reference's
+    `flag <= 0` branch and the answer depends on the last bit of cos(theta)."""
+    out = {}
+    x, box = L.fcc(3, 3, 3)
+    out["fcc3_perturbed"] = (L.build_config(L.perturb(x, 0.05, 12345), box, 6.5, shuffle_rows=7), ["Ni"])
+    x2, box2 = L.fcc(3, 3, 4)
+    out["fcc334_hot"] = (L.build_config(L.perturb(x2, 0.15, 99), box2, 6.5, shuffle_rows=3), ["Ni"])
+    xc, _ = L.fcc(2, 2, 2)
+    xc = L.perturb(xc, 0.08, 5)
+    xc = np.concatenate([xc, [[40.0, 40.0, 40.0]], [[46.0, 40.0, 40.0]], [[42.5, 40.0, 40.0]], [[41.2, 42.0, 40.3]]])
+    out["cluster_ragged"] = (L.build_config(xc, np.array([100.0, 100.0, 100.0]), 6.5, periodic=(False, False, False)), ["Ni"])
+    rng = np.random.default_rng(11)
+    types = rng.integers(1, 3, size=len(x)).astype(np.int32)
+    out["fcc3_two_types"] = (L.build_config(L.perturb(x, 0.05, 777), box, 6.5, types=types), ["Ni", "Ni"])
+    return out
+
+
+def anna_cases():
+    out = {}
+    rc = 5.055
+    x, box = L.bcc(4, 4, 4)
+    out["bcc4_perfect"] = (L.build_config(x, box, rc), ["Fe"])
+    out["bcc4_perturbed"] = (L.build_config(L.perturb(x, 0.05, 12345), box, rc, shuffle_rows=7), ["Fe"])
+    x3, box3 = L.bcc(3, 3, 4)
+    out["bcc334_hot"] = (L.build_config(L.perturb(x3, 0.15, 99), box3, rc, shuffle_rows=3), ["Fe"])
+    xc, _ = L.bcc(3, 3, 3)
+    xc = L.perturb(xc, 0.08, 5)
+    xc = np.concatenate([xc, [[40.0, 40.0, 40.0]], [[44.5, 40.0, 40.0]], [[44.5, 43.5, 40.0]]])
+    out["cluster_ragged"] = (L.build_config(xc, np.array([100.0, 100.0, 100.0]), rc, periodic=(False, False, False)), ["Fe"])
+    rng = np.random.default_rng(11)
+    types = rng.integers(1, 3, size=128).astype(np.int32)
+    out["bcc4_two_types"] = (L.build_config(L.perturb(x, 0.05, 777), box, rc, types=types), ["Fe", "Fe"])
+    x8, box8 = L.bcc(8, 8, 8)
+    out["bcc8_perturbed"] = (L.build_config(L.perturb(x8, 0.05, 2024), box8, rc), ["Fe"])
+    return out
+
+
+def dump_kind(kind, prefix, potfile, cases_fn):
+    for name, (cfg, elems) in cases_fn().items():
+        r1 = run_reference(kind, cfg, potfile, elems, eflag=3, vflag=1 + 4)
+        r2 = run_reference(kind, cfg, potfile, elems, eflag=3, vflag=2)
+        assert np.array_equal(r1["f"], r2["f"])
+        np.savez_compressed(
+            os.path.join(OUT, f"{prefix}_{name}.npz"),
+            nlocal=cfg.nlocal, nghost=cfg.nghost, x=cfg.x, type=cfg.type, ghost_owner=cfg.ghost_owner,
+            ilist=cfg.ilist, numneigh=cfg.numneigh, neigh=cfg.neigh, box=cfg.box, elements=np.array(elems),
+            eng_vdwl=r1["eng_vdwl"], eatom=r1["eatom"], f=r1["f"], virial_pair=r1["virial"], virial_fdotr=r2["virial"],
+            vatom=r1["vatom"], ref_seconds=r1["seconds"])
+        print(f"{prefix} {name}: nlocal {cfg.nlocal} nghost {cfg.nghost} E/atom {r1['eng_vdwl'] / cfg.nlocal:.10f} "
+              f"fmax {np.abs(cfg.fold(r1['f'])).max():.6e} ({r1['seconds']:.1f} s)")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ni_anna":      # only the round-1b additions
+        dump_ni_anna_potentials()
+        dump_kind("annp_ni", "annp_ni", NI_POT, ni_cases)
+        dump_kind("anna_adp", "anna_adp", ANNA_POT, anna_cases)
+        sys.exit(0)
     dump_potential()
+    dump_ni_anna_potentials()
+    dump_kind("annp_ni", "annp_ni", NI_POT, ni_cases)
+    dump_kind("anna_adp", "anna_adp", ANNA_POT, anna_cases)
     dump_fe_st()
     dump_cases()

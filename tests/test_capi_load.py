@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "annp_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(annp_b200_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(ann[pa]_b200_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_symbols_are_exported(built):

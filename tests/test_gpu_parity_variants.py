@@ -1,0 +1,131 @@
+"""Parity of the CUDA path for the other two copies of the reference style: the Ni `annp` copy (Behler-Parrinello
+descriptor, BASELINE config 2) and ANNA-ADP (`pair_style anna_adp/gpu`).  Run with -m gpu.
+
+Golden vectors: tests/golden/annp_ni_*.npz, anna_adp_*.npz, produced by the UNMODIFIED reference sources
+(ref_annp_ni / ref_anna_adp, see make_golden.py).  Tolerances asserted (north_star: energy <= 1e-6 relative,
+forces <= 1e-5 eV/A):
+    Ni    per-atom energy <= 1e-10 (raw network output, ~0.76), forces <= 1e-9 eV/A, virial <= 1e-9
+    ANNA  per-atom energy <= 1e-9 eV,  forces <= 1e-9 eV/A, virial <= 1e-8 eV
+"""
+import numpy as np
+import pytest
+
+import util
+from meng_zhang_b200 import capi, lattice as L
+from meng_zhang_b200.pair import PairANNPGPU, read_potential
+from meng_zhang_b200.pair_anna import PairANNAADPGPU, read_anna_potential
+
+pytestmark = pytest.mark.gpu
+
+
+def make_ni(pot_file, elems=("Ni",)):
+    pair = PairANNPGPU(ntypes=len(elems))            # variant decided from the file (coefficient blocks -> Ni copy)
+    pair.settings([])
+    pair.coeff(["*", "*", pot_file] + list(elems))
+    pair.init_style()
+    return pair
+
+
+def make_anna(pot_file, elems=("Fe",)):
+    pair = PairANNAADPGPU(ntypes=len(elems))
+    pair.settings([])
+    pair.coeff(["*", "*", pot_file] + list(elems))
+    pair.init_style()
+    return pair
+
+
+@pytest.mark.parametrize("name", util.NI_CASES)
+def test_ni_golden_case(name, ni_pot_file):
+    cfg, elems, ref = util.load_case(name, "annp_ni")
+    pair = make_ni(ni_pot_file, elems)
+    f = pair.compute(3, 1 + 4, cfg, ago=0)
+    assert np.abs(pair.eatom - ref["eatom"]).max() <= 1e-10
+    assert abs(pair.eng_vdwl - ref["eng_vdwl"]) <= 1e-9
+    assert np.abs(f - ref["f"]).max() <= 1e-9
+    assert np.abs(pair.virial - ref["virial_pair"]).max() <= 1e-9
+    assert np.abs(pair.vatom - ref["vatom"]).max() <= 1e-9
+    f2 = pair.compute(3, 1 + 4, cfg, ago=1)
+    assert np.array_equal(f, f2)                       # deterministic
+    assert np.array_equal(f, pair.compute(0, 0, cfg, ago=1))
+    pair.clear()
+
+
+@pytest.mark.parametrize("name", util.ANNA_CASES)
+def test_anna_golden_case(name, anna_pot_file):
+    cfg, elems, ref = util.load_case(name, "anna_adp")
+    pair = make_anna(anna_pot_file, elems)
+    f = pair.compute(3, 1 + 4, cfg, ago=0)
+    assert np.abs(pair.eatom - ref["eatom"]).max() <= 1e-9
+    assert abs(pair.eng_vdwl - ref["eng_vdwl"]) <= 1e-12 * abs(ref["eng_vdwl"]) + 1e-9
+    assert np.abs(f - ref["f"]).max() <= 1e-9
+    assert np.abs(pair.virial - ref["virial_pair"]).max() <= 1e-8
+    assert np.abs(pair.virial - ref["virial_fdotr"]).max() <= 1e-8
+    assert np.abs(pair.vatom - ref["vatom"]).max() <= 1e-9
+    f2 = pair.compute(3, 1 + 4, cfg, ago=1)
+    assert np.array_equal(f, f2)
+    assert np.array_equal(f, pair.compute(0, 0, cfg, ago=1))
+    pair.clear()
+
+
+def test_ni_against_live_oracle_32000_atom_geometry_sample(ni_pot_file):
+    """BASELINE config 2 geometry (fcc Ni, a = 3.52) at a size the oracle finishes in seconds: 6^3 cells = 864 atoms,
+    thermal displacements."""
+    from oracle import restatement
+    x, box = L.fcc(6, 6, 6)
+    cfg = L.build_config(L.perturb(x, 0.07, 2718), box, 6.5, shuffle_rows=5)
+    pair = make_ni(ni_pot_file)
+    f = pair.compute(3, 1, cfg, ago=0)
+    ref = restatement.compute_ni(read_potential(ni_pot_file, ["Ni"]), cfg, nthreads=4, dump_G=True)
+    assert np.abs(f - ref["f"]).max() <= 1e-9
+    assert np.abs(pair.eatom - ref["eatom"]).max() <= 1e-10
+    assert np.abs(pair.virial - ref["virial"]).max() <= 1e-8
+    G, _ = pair.descriptors(cfg)
+    assert np.abs(G - ref["G"]).max() <= 1e-11
+    assert np.abs(f.sum(axis=0)).max() < 1e-9          # momentum conservation (each pair force is applied +/-)
+    pair.clear()
+
+
+def test_anna_against_live_oracle_and_network_outputs(anna_pot_file):
+    from oracle import restatement
+    x, box = L.bcc(5, 4, 3)
+    cfg = L.build_config(L.perturb(x, 0.12, 2718), box, 5.055, shuffle_rows=5)
+    pair = make_anna(anna_pot_file)
+    f = pair.compute(3, 1, cfg, ago=0)
+    ref = restatement.compute_anna(read_anna_potential(anna_pot_file, ["Fe"]), cfg, nthreads=4, dump_G=True)
+    assert np.abs(f - ref["f"]).max() <= 1e-9
+    assert np.abs(pair.eatom - ref["eatom"]).max() <= 1e-9
+    G, lp = pair.descriptors(cfg)                       # for ANNA the second array carries (d2, q2) in columns 0, 1
+    assert np.abs(G - ref["G"]).max() <= 1e-10
+    assert np.abs(lp[:, :2] - ref["lparams"]).max() <= 1e-12
+    pair.clear()
+
+
+def test_variants_empty_and_isolated_atoms(ni_pot_file, anna_pot_file):
+    from oracle import restatement
+    one = L.build_config(np.array([[5.0, 5.0, 5.0]]), np.array([50.0, 50, 50]), 6.5, periodic=(False, False, False))
+    pair = make_ni(ni_pot_file)
+    f = pair.compute(3, 1, one, ago=0)
+    ref = restatement.compute_ni(read_potential(ni_pot_file, ["Ni"]), one)
+    assert np.all(f == 0.0) and abs(pair.eng_vdwl - ref["eng_vdwl"]) <= 1e-12
+    pair.clear()
+    # ANNA: an isolated atom has rho = 0 -> sqrt(0) in the energy, 0 * inf never formed because there is no neighbour
+    pair = make_anna(anna_pot_file)
+    f = pair.compute(3, 1, one, ago=0)
+    ref = restatement.compute_anna(read_anna_potential(anna_pot_file, ["Fe"]), one)
+    assert np.all(f == 0.0) and abs(pair.eng_vdwl - ref["eng_vdwl"]) <= 1e-9
+    for pts in ([[5, 5, 5], [7.4, 5, 5]], [[5, 5, 5], [7.4, 5, 5], [6.0, 7.2, 5.3]]):
+        c = L.build_config(np.array(pts, dtype=float), np.array([50.0, 50, 50]), 5.055, periodic=(False, False, False))
+        f = pair.compute(3, 1, c, ago=0)
+        ref = restatement.compute_anna(read_anna_potential(anna_pot_file, ["Fe"]), c)
+        assert np.abs(f - ref["f"]).max() <= 1e-9 and np.abs(pair.eatom - ref["eatom"]).max() <= 1e-9
+    pair.clear()
+
+
+def test_explicit_variant_overrides_and_rejects(fe_pot_file):
+    """A Fe file has no coefficient blocks: asking for the Ni copy on it is an error, not a silent fallback."""
+    from meng_zhang_b200.pair import LammpsError
+    pair = PairANNPGPU(ntypes=1, variant=capi.VARIANT_NI)
+    pair.settings([])
+    pair.coeff(["*", "*", fe_pot_file, "Fe"])
+    with pytest.raises(LammpsError):
+        pair.init_style()
