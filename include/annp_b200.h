@@ -75,6 +75,9 @@ typedef struct annp_b200_handle_s *annp_b200_handle;
 /*   VARIANT_ANNA_ADP  anna-gpu-lammps/bcc_fe (`pair_style anna_adp/gpu`): handles of this kind are created by
  *               anna_b200_init below; every other entry point (neigh, compute, halo, ...) is shared */
 #define ANNP_B200_VARIANT_ANNA_ADP 2
+/* or'ed into params.variant: run the generic Behler-Parrinello kernel even when the coefficient table has the product
+ * structure the fast kernel is specialised for (used by the tests to keep both kernels covered) */
+#define ANNP_B200_VARIANT_FLAG_GENERIC 0x100
 
 /*
  * Flat parameter block == the argument list of annp_gpu_init (src/pair_annp_gpu.cpp:31-39).

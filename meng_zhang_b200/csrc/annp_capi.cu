@@ -17,6 +17,7 @@ size_t annp_force_smem_bytes(const DevParams &hp, int capacity);
 bool annp_force_supported(int npsf, int ntsf);
 cudaError_t annp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream, int *blocks_out);
 cudaError_t annp_bp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream);
+int annp_bp_layout(const DevParams &hp);
 void aux_pack_xq(const double *x, const int *type, double4 *xq, int nall, cudaStream_t s);
 void aux_build_reverse(const int *nbr, long long total, int nall, long long *rev_off, int *rev_pos, int *cnt, int *tmp,
                        long long *tile_sum, cudaStream_t s);
@@ -427,8 +428,9 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
   if (!p || !out) { set_err(err, errlen, "null argument"); return ANNP_B200_EINVAL; }
   *out = nullptr;
   if (p->abi_version != ANNP_B200_ABI_VERSION) { set_err(err, errlen, "ABI version mismatch"); return ANNP_B200_EINVAL; }
-  const bool ni = p->variant == ANNP_B200_VARIANT_NI;
-  if (p->variant != ANNP_B200_VARIANT_FE && !ni) { set_err(err, errlen, "unknown variant (ANNA-ADP handles are created by anna_b200_init)"); return ANNP_B200_EINVAL; }
+  const int variant = p->variant & 0xff;
+  const bool ni = variant == ANNP_B200_VARIANT_NI;
+  if (variant != ANNP_B200_VARIANT_FE && !ni) { set_err(err, errlen, "unknown variant (ANNA-ADP handles are created by anna_b200_init)"); return ANNP_B200_EINVAL; }
   // the Ni files still say "Chebyshev" on their keyword line; the Ni copy of the style ignores flagsym altogether
   if (!ni && p->flagsym != ANNP_B200_SYM_CHEBYSHEV) { set_err(err, errlen, "only the Chebyshev descriptor (flagsym 0) is implemented for the Fe copy"); return ANNP_B200_EINVAL; }
   if (!valid_shape(p->ntypes, p->nelements, p->ntl, p->nnod, p->nsf, p->npsf, p->ntsf)) {
@@ -448,7 +450,7 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
   rc = fill_network(h, p->ntypes, p->nelements, p->ntl, p->nnod, 1, p->nsf, p->npsf, p->ntsf, p->flagact, p->cutsq, p->map, p->cut, err, errlen);
   if (rc) { annp_b200_clear(h); return rc; }
   DevParams &hp = h->hp;
-  hp.variant = p->variant;
+  hp.variant = variant;
   hp.e_scale = p->e_scale; hp.e_shift = p->e_shift; hp.e_atom = p->e_atom;
   for (int n = 0; n < p->nsf; n++) { hp.sf_scale[n] = p->sfnor_scal[n]; hp.sf_avg[n] = p->sfnor_avg[n]; }
   if (ni) {
@@ -458,6 +460,7 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
       hp.ang_eta[n] = p->sym_coeang[n * 4 + 0]; hp.ang_lambda[n] = p->sym_coeang[n * 4 + 1]; hp.ang_zeta[n] = p->sym_coeang[n * 4 + 2];
     }
     hp.ang_rc = p->sym_coeang[3];                          // ni/src/pair_annp.cpp:731
+    hp.bp_layout = (p->variant & ANNP_B200_VARIANT_FLAG_GENERIC) ? 0 : annp_bp_layout(hp);
   }
   rc = upload_params(h, p->weights, p->bias, !ni, err, errlen);
   if (rc) { annp_b200_clear(h); return rc; }

@@ -30,6 +30,7 @@ struct DevParams {
   int variant;
   double rad_eta[ANNP_B200_MAX_SF], rad_rc;                    // radial: eta_m, common Rc (Bohr)
   double ang_eta[ANNP_B200_MAX_SF], ang_lambda[ANNP_B200_MAX_SF], ang_zeta[ANNP_B200_MAX_SF], ang_rc;
+  int bp_layout;                                               // 1: product-structured table -> annp_bp_fast_kernel (annp_bp_layout)
   // ANNP_B200_VARIANT_ANNA_ADP: the 17 global ADP parameters and the energy offset (pair_anna_adp.cpp:97-103)
   double gparams[17], e_base;
 };

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kWarps * 32) annp_bp_force_kernel(const ForceA
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const DevParams &P = *a.prm;
   const int C = a.capacity;
-  const int nsf = P.nsf, npsf = P.npsf, ntsf = P.ntsf, nnod = P.nnod, nl = P.nlayers;
+  const int nsf = P.nsf, npsf = P.npsf, nnod = P.nnod, nl = P.nlayers;
   const int wtot = P.nelements * P.w_per_elem, btot = P.nelements * P.b_per_elem;
 
   double *sW = reinterpret_cast<double *>(smem_raw);
@@ -284,7 +284,325 @@ __global__ void __launch_bounds__(kWarps * 32) annp_bp_force_kernel(const ForceA
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path for coefficient tables with product structure (the shipped ni_annp_potential_2.ann):
+//     n = (e * NZ + z) * 2 + l,   eta = eta_e (e < NE),  zeta = 2^kZetaLog2[z],  lambda = -1 (l = 0), +1 (l = 1)
+// annp_bp_layout() verifies this at init; any other table runs the generic kernel above.
+//   * (1 + lambda cos)^zeta by repeated squaring and one exp per distinct eta instead of 2 pow + 1 exp per component
+//   * the gradient of a triplet needs only three sums over the components,
+//         S1 = sum_n c_n lambda_n zeta_n T_n / flag_n,  S2 = sum_n c_n eta_n T_n,  S3 = sum_n c_n T_n,
+//     (T_n = 2^(1-zeta) flag^zeta exp(-eta R2)), followed by ONE vector assembly
+//   * forward and backward are both organised "lane <-> neighbour a, loop over partners b" so every lane only ever
+//     adds into its own registers: no scatter, no atomics, fixed summation order.
+template <int NZ> __host__ __device__ constexpr int bp_zeta_log2(int z);
+template <> __host__ __device__ constexpr int bp_zeta_log2<4>(int z) { return z == 0 ? 0 : (z == 1 ? 1 : (z == 2 ? 2 : 4)); }   // zeta = 1, 2, 4, 16
+
+struct BpGeom {        // neighbour as cached by the fast kernel
+  double ux, uy, uz;   // unit vector of x_i - x_j
+  double r;            // Angstrom
+  double fc, dfc;      // angular cutoff function of r*CFLENGTH
+};
+
+// primitives of the pair (a, b): returns false when the triplet does not contribute
+template <int NE>
+__device__ __forceinline__ bool bp_pair_prims(const BpGeom &A, const BpGeom &B, double Rc, double rcinv, const double *eta,
+                                              double &cosv, double &rjk, double &fcjk, double &dfcjk, double (&E)[NE],
+                                              double &ex, double &ey, double &ez) {
+  // e = x_a - x_b (positions) = (x_i - x_b) - (x_i - x_a)
+  ex = B.r * B.ux - A.r * A.ux; ey = B.r * B.uy - A.r * A.uy; ez = B.r * B.uz - A.r * A.uz;
+  const double r2 = ex * ex + ey * ey + ez * ez;
+  rjk = sqrt(r2);
+  const double rjk_m = rjk * CFLENGTH;
+  if (!(rjk_m < Rc)) return false;
+  double sn, cs;
+  sincospi(rjk_m * rcinv, &sn, &cs);
+  fcjk = 0.5 * (cs + 1.0);
+  dfcjk = -0.5 * kPi * rcinv * sn;
+  cosv = A.ux * B.ux + A.uy * B.uy + A.uz * B.uz;
+  const double ra = A.r * CFLENGTH, rb = B.r * CFLENGTH;
+  const double r2sum = ra * ra + rb * rb + rjk_m * rjk_m;
+#pragma unroll
+  for (int e = 0; e < NE; e++) E[e] = exp(-eta[e] * r2sum);
+  return true;
+}
+
+template <int NE, int NZ>
+__global__ void __launch_bounds__(kWarps * 32, 3) annp_bp_fast_kernel(const ForceArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = NE * NZ * 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const DevParams &P = *a.prm;
+  const int C = a.capacity;
+  const int nsf = P.nsf, npsf = P.npsf, nnod = P.nnod, nl = P.nlayers;
+  const int wtot = P.nelements * P.w_per_elem, btot = P.nelements * P.b_per_elem;
+
+  double *sW = reinterpret_cast<double *>(smem_raw);
+  double *sBias = sW + wtot;
+  double *blk_end = sBias + btot;
+  for (int t = threadIdx.x; t < wtot; t += blockDim.x) sW[t] = P.weights[t];
+  for (int t = threadIdx.x; t < btot; t += blockDim.x) sBias[t] = P.bias[t];
+  const size_t per_warp_doubles = (size_t) 6 * C + 3 * nsf + (size_t) 2 * nl * nnod + 2 * nnod;
+  size_t warp_bytes = per_warp_doubles * sizeof(double) + (size_t) C * sizeof(int);
+  warp_bytes = (warp_bytes + 15) & ~(size_t) 15;
+  const size_t blk_bytes = ((size_t) ((unsigned char *) blk_end - smem_raw) + 15) & ~(size_t) 15;
+  unsigned char *wbase = smem_raw + blk_bytes + (size_t) warp * warp_bytes;
+  BpGeom *sN = reinterpret_cast<BpGeom *>(wbase);
+  double *sG = reinterpret_cast<double *>(sN + C);
+  double *sdE = sG + nsf;
+  double *sCn = sdE + nsf;
+  double *sH = sCn + nsf;
+  double *sHd = sH + nl * nnod;
+  double *sDel = sHd + nl * nnod;
+  int *spos = reinterpret_cast<int *>(sDel + 2 * nnod);
+  __syncthreads();
+
+  const double Rc_rad = P.rad_rc, Rc = P.ang_rc, rcinv = 1.0 / Rc;
+  const double Rc_max = fmax(Rc_rad, Rc);
+  double eta[NE];
+#pragma unroll
+  for (int e = 0; e < NE; e++) eta[e] = P.ang_eta[e * NZ * 2];
+
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(&a.cnt->work, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= (unsigned long long) a.inum) break;
+    const int ii = (int) item;
+    const int i = a.ilist[ii];
+    const double4 xi = a.xq[i];
+    const int ti = (int) xi.w;
+    const long long p0 = a.row_off[ii];
+    const int L = (int) (a.row_off[ii + 1] - p0);
+
+    // ---- 1. filter (list order kept): r * CFLENGTH < Rc, no pair-level list cutoff (ni/src/pair_annp.cpp:126-140)
+    int N = 0;
+    for (int base = 0; base < L; base += 32) {
+      const int q = base + lane;
+      const bool valid = q < L;
+      bool in = false;
+      double dx = 0, dy = 0, dz = 0, r = 0;
+      if (valid) {
+        const int j = a.nbr[p0 + q] & ANNP_NEIGHMASK;
+        const double4 xj = a.xq[j];
+        dx = xi.x - xj.x; dy = xi.y - xj.y; dz = xi.z - xj.z;
+        r = sqrt(dx * dx + dy * dy + dz * dz);
+        in = (r * CFLENGTH < Rc_max);
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, in);
+      const int slot = N + __popc(mask & ((1u << lane) - 1u));
+      if (in && slot < C) {
+        BpGeom g;
+        const double rinv = 1.0 / r;
+        g.ux = dx * rinv; g.uy = dy * rinv; g.uz = dz * rinv; g.r = r;
+        double sn, cs;
+        sincospi(r * CFLENGTH * rcinv, &sn, &cs);
+        g.fc = 0.5 * (cs + 1.0);
+        g.dfc = -0.5 * kPi * rcinv * sn;
+        sN[slot] = g;
+        spos[slot] = q;
+      } else if (valid) {
+        a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (a.vpair) {
+          double *vp = a.vpair + (size_t) (p0 + q) * 6;
+#pragma unroll
+          for (int k = 0; k < 6; k++) vp[k] = 0.0;
+        }
+      }
+      N += __popc(mask);
+    }
+    if (lane == 0) {
+      atomicMax(&a.cnt->max_neigh, N);
+      atomicAdd(&a.cnt->sum_neigh, (unsigned long long) N);
+      atomicAdd(&a.cnt->sum_trip, (unsigned long long) N * (unsigned long long) (N > 0 ? N - 1 : 0) / 2ull);
+    }
+    if (N > C) {
+      if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
+      for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+      __syncwarp();
+      continue;
+    }
+    __syncwarp();
+
+    // ---- 2. forward.  radial: one lane per neighbour, one butterfly per component
+    for (int m = 0; m < npsf; m++) {
+      double acc = 0.0;
+      for (int s = lane; s < N; s += 32) {
+        const BpGeom g = sN[s];
+        const double rm = g.r * CFLENGTH;
+        if (rm < Rc_rad) {
+          double fc, dfc;
+          bp_fc(rm, Rc_rad, fc, dfc);
+          acc += exp(-P.rad_eta[m] * rm * rm) * fc;                      // pair_annp.cpp:697-703
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) sG[m] = (acc - P.sf_avg[m]) * P.sf_scale[m];
+    }
+    // angular: lane <-> first member a, partners b > a (the reference's kk > jj)
+    double G[NT];
+#pragma unroll
+    for (int n = 0; n < NT; n++) G[n] = 0.0;
+    for (int s = lane; s < N; s += 32) {
+      const BpGeom A = sN[s];
+      if (!(A.r * CFLENGTH < Rc)) continue;
+      for (int b = s + 1; b < N; b++) {
+        const BpGeom B = sN[b];
+        if (!(B.r * CFLENGTH < Rc)) continue;
+        double cosv, rjk, fcjk, dfcjk, E[NE], ex, ey, ez;
+        if (!bp_pair_prims<NE>(A, B, Rc, rcinv, eta, cosv, rjk, fcjk, dfcjk, E, ex, ey, ez)) continue;
+        const double tfc = A.fc * B.fc * fcjk;
+        const double fm = 1.0 - cosv, fp = 1.0 + cosv;                    // lambda = -1, +1
+        double pm = fm > 0.0 ? fm : 0.0, pp = fp > 0.0 ? fp : 0.0;       // flag <= 0: the term is skipped (:748-751)
+        int lg = 0;
+#pragma unroll
+        for (int z = 0; z < NZ; z++) {
+          while (lg < bp_zeta_log2<NZ>(z)) { pm *= pm; pp *= pp; lg++; }
+          const double coef = ldexp(1.0, 1 - (1 << bp_zeta_log2<NZ>(z)));   // 2^(1 - zeta)
+#pragma unroll
+          for (int e = 0; e < NE; e++) {
+            const double w = coef * E[e] * tfc;
+            G[(e * NZ + z) * 2 + 0] = fma(w, pm, G[(e * NZ + z) * 2 + 0]);
+            G[(e * NZ + z) * 2 + 1] = fma(w, pp, G[(e * NZ + z) * 2 + 1]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+      const double v = warp_sum(G[n]);
+      if (lane == 0) sG[npsf + n] = (v - P.sf_avg[npsf + n]) * P.sf_scale[npsf + n];   // (G - min)/(max - min), :168-170
+    }
+    __syncwarp();
+
+    // ---- 3. MLP (raw output is the energy, :858-860)
+    const int elem = P.map[ti];
+    const double out = annp_mlp_warp(P, sW + elem * P.w_per_elem, sBias + elem * P.b_per_elem, sG, sdE, sH, sHd, sDel, lane);
+    const double e_i = out;
+    if (a.G_dbg) for (int n = lane; n < nsf; n += 32) { a.G_dbg[(size_t) ii * nsf + n] = sG[n]; a.dEdG_dbg[(size_t) ii * nsf + n] = sdE[n]; }
+    for (int n = lane; n < nsf; n += 32) sCn[n] = sdE[n] * P.sf_scale[n];
+    __syncwarp();
+    double c[NT];
+#pragma unroll
+    for (int n = 0; n < NT; n++) c[n] = sCn[npsf + n];
+
+    // ---- 4. backward: lane <-> neighbour s, all partners b
+    double fix = 0, fiy = 0, fiz = 0;
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
+    for (int s = lane; s < N; s += 32) {
+      const BpGeom A = sN[s];
+      double gx = 0, gy = 0, gz = 0;                   // d out / d x_s in the reference's units (per Bohr)
+      const double ra_m = A.r * CFLENGTH;
+      if (ra_m < Rc_rad) {                             // annp_symmetry_pair, :686-708
+        double fc, dfc;
+        bp_fc(ra_m, Rc_rad, fc, dfc);
+        double acc = 0.0;
+        for (int m = 0; m < npsf; m++) {
+          const double et = P.rad_eta[m];
+          acc = fma(sCn[m], exp(-et * ra_m * ra_m) * (-fc * 2.0 * et * ra_m + dfc), acc);
+        }
+        gx = -acc * A.ux; gy = -acc * A.uy; gz = -acc * A.uz;      // dr/dx_j = -u
+      }
+      if (ra_m < Rc) {
+        for (int b = 0; b < N; b++) {
+          if (b == s) continue;
+          const BpGeom B = sN[b];
+          if (!(B.r * CFLENGTH < Rc)) continue;
+          const bool first = s < b;                    // s is the reference's j (first) or k (second) of the pair
+          double cosv, rjk, fcjk, dfcjk, E[NE], ex, ey, ez;
+          // primitives are symmetric in (a, b) except e = x_a - x_b: evaluate them with (first, second) = (j, k)
+          const bool ok = first ? bp_pair_prims<NE>(A, B, Rc, rcinv, eta, cosv, rjk, fcjk, dfcjk, E, ex, ey, ez)
+                                : bp_pair_prims<NE>(B, A, Rc, rcinv, eta, cosv, rjk, fcjk, dfcjk, E, ex, ey, ez);
+          if (!ok) continue;
+          const double tfc = A.fc * B.fc * fcjk;
+          const double fm = 1.0 - cosv, fp = 1.0 + cosv;
+          const bool okm = fm > 0.0, okp = fp > 0.0;
+          double pm = okm ? fm : 0.0, pp = okp ? fp : 0.0;
+          const double im = okm ? 1.0 / fm : 0.0, ip = okp ? 1.0 / fp : 0.0;
+          double S1 = 0.0, S2 = 0.0, S3 = 0.0;
+          int lg = 0;
+#pragma unroll
+          for (int z = 0; z < NZ; z++) {
+            while (lg < bp_zeta_log2<NZ>(z)) { pm *= pm; pp *= pp; lg++; }
+            const double zeta = (double) (1 << bp_zeta_log2<NZ>(z));
+            const double coef = ldexp(1.0, 1 - (1 << bp_zeta_log2<NZ>(z)));
+            double tm = 0.0, tp = 0.0, um = 0.0, up = 0.0;   // sum_e c E (and eta-weighted) for lambda = -1 / +1
+#pragma unroll
+            for (int e = 0; e < NE; e++) {
+              const double cm = c[(e * NZ + z) * 2 + 0] * E[e], cp = c[(e * NZ + z) * 2 + 1] * E[e];
+              tm += cm; tp += cp;
+              um = fma(eta[e], cm, um); up = fma(eta[e], cp, up);
+            }
+            const double Tm = coef * pm, Tp = coef * pp;
+            S3 = fma(Tm, tm, fma(Tp, tp, S3));
+            S2 = fma(Tm, um, fma(Tp, up, S2));
+            S1 = fma(zeta * Tp * ip, tp, fma(-zeta * Tm * im, tm, S1));     // lambda zeta T / flag
+          }
+          const double k1 = S1 * tfc / CFLENGTH, k2 = S2 * tfc;
+          // geometry of the member being differentiated (me) and of the other one (ot); e = x_j - x_k
+          const double mr = A.r, orr = B.r;
+          const double mx = A.ux, my = A.uy, mz = A.uz, ox = B.ux, oy = B.uy, oz = B.uz;
+          const double rinv = 1.0 / mr, rjkinv = 1.0 / rjk;
+          const double djx = ex * rjkinv, djy = ey * rjkinv, djz = ez * rjkinv;   // dr_djk = (x_j - x_k)/r_jk
+          const double sgn = first ? 1.0 : -1.0;
+          // d cos / d x_me = (-u_ot + cos u_me) / r_me
+          const double cx = (cosv * mx - ox) * rinv, cy = (cosv * my - oy) * rinv, cz = (cosv * mz - oz) * rinv;
+          // term2: 2 (r_me_m dr_dme +- r_IK_m dr_djk) -- r_ik in both, as the reference (:734-735)
+          const double rik_m = (first ? orr : mr) * CFLENGTH, rme_m = mr * CFLENGTH;
+          const double t2x = 2.0 * (rme_m * (-mx) + sgn * rik_m * djx);
+          const double t2y = 2.0 * (rme_m * (-my) + sgn * rik_m * djy);
+          const double t2z = 2.0 * (rme_m * (-mz) + sgn * rik_m * djz);
+          // term3: fc_ot (dfc_me dr_dme fc_jk +- fc_me dfc_jk dr_djk)
+          const double q1 = B.fc * A.dfc * fcjk, q2 = sgn * B.fc * A.fc * dfcjk;
+          const double t3x = q1 * (-mx) + q2 * djx, t3y = q1 * (-my) + q2 * djy, t3z = q1 * (-mz) + q2 * djz;
+          gx += k1 * cx - k2 * t2x + S3 * t3x;
+          gy += k1 * cy - k2 * t2y + S3 * t3y;
+          gz += k1 * cz - k2 * t2z + S3 * t3z;
+        }
+      }
+      const double Fx = -gx, Fy = -gy, Fz = -gz;       // Fj of the reference before CFFORCE (:180-190)
+      const int q = spos[s];
+      a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
+      fix -= Fx * CFFORCE; fiy -= Fy * CFFORCE; fiz -= Fz * CFFORCE;
+      if (a.vir_c || a.vpair) {
+        const double X = A.r * A.ux, Y = A.r * A.uy, Z = A.r * A.uz;
+        const double w0 = -X * Fx, w1 = -Y * Fy, w2 = -Z * Fz, w3 = -X * Fy, w4 = -X * Fz, w5 = -Y * Fz;
+        v0 += w0; v1 += w1; v2 += w2; v3 += w3; v4 += w4; v5 += w5;
+        if (a.vpair) {
+          double *vp = a.vpair + (size_t) (p0 + q) * 6;
+          vp[0] = w0; vp[1] = w1; vp[2] = w2; vp[3] = w3; vp[4] = w4; vp[5] = w5;
+        }
+      }
+    }
+    fix = warp_sum(fix); fiy = warp_sum(fiy); fiz = warp_sum(fiz);
+    if (lane == 0) a.fself[ii] = make_double4(fix, fiy, fiz, e_i);
+    if (a.vir_c) {
+      v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
+      v3 = warp_sum(v3); v4 = warp_sum(v4); v5 = warp_sum(v5);
+      if (lane == 0) {
+        double *vc = a.vir_c + (size_t) ii * 6;
+        vc[0] = v0; vc[1] = v1; vc[2] = v2; vc[3] = v3; vc[4] = v4; vc[5] = v5;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 }    // namespace
+
+// 1 when the angular table has the product structure the fast kernel is instantiated for, else 0 (generic kernel)
+int annp_bp_layout(const DevParams &hp) {
+  const int NE = 3, NZ = 4;
+  static const double zetas[4] = {1.0, 2.0, 4.0, 16.0};
+  if (hp.ntsf != NE * NZ * 2) return 0;
+  for (int e = 0; e < NE; e++)
+    for (int z = 0; z < NZ; z++)
+      for (int l = 0; l < 2; l++) {
+        const int n = (e * NZ + z) * 2 + l;
+        if (hp.ang_eta[n] != hp.ang_eta[e * NZ * 2] || hp.ang_zeta[n] != zetas[z] || hp.ang_lambda[n] != (l ? 1.0 : -1.0)) return 0;
+      }
+  return 1;
+}
 
 size_t annp_bp_smem_bytes(const DevParams &hp, int capacity) {
   size_t blk = (size_t) (hp.nelements * (hp.w_per_elem + hp.b_per_elem)) * sizeof(double);
@@ -296,16 +614,17 @@ size_t annp_bp_smem_bytes(const DevParams &hp, int capacity) {
 
 cudaError_t annp_bp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream) {
   const size_t smem = annp_bp_smem_bytes(hp, args.capacity);
-  cudaError_t e = cudaFuncSetAttribute(annp_bp_force_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  void (*kern)(const ForceArgs) = hp.bp_layout == 1 ? annp_bp_fast_kernel<3, 4> : annp_bp_force_kernel;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, annp_bp_force_kernel, kWarps * 32, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarps * 32, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
   long long want = ((long long) args.inum + kWarps - 1) / kWarps;
   long long blocks = (long long) per_sm * num_sms;
   if (blocks > want) blocks = want;
   if (blocks < 1) blocks = 1;
-  annp_bp_force_kernel<<<(unsigned) blocks, kWarps * 32, smem, stream>>>(args);
+  kern<<<(unsigned) blocks, kWarps * 32, smem, stream>>>(args);
   return cudaGetLastError();
 }

@@ -253,7 +253,7 @@ class PairANNPGPU:
                     self.cutsq[i, j] = self.cutsq[j, i] = 0.0
         w, b = p.flat_weights()
         variant = p.variant if self.variant is None else self.variant
-        if variant == capi.VARIANT_NI:
+        if (variant & 0xff) == capi.VARIANT_NI:
             if p.sym_coerad is None:
                 raise LammpsError("potential file has no symmetry-function coefficient blocks (needed by the Ni copy)")
             # (G - sf_min) / (sf_max - sf_min), ni/src/pair_annp.cpp:99-101,168-170

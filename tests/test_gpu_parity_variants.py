@@ -18,8 +18,9 @@ from meng_zhang_b200.pair_anna import PairANNAADPGPU, read_anna_potential
 pytestmark = pytest.mark.gpu
 
 
-def make_ni(pot_file, elems=("Ni",)):
-    pair = PairANNPGPU(ntypes=len(elems))            # variant decided from the file (coefficient blocks -> Ni copy)
+def make_ni(pot_file, elems=("Ni",), generic=False):
+    # variant decided from the file (coefficient blocks -> Ni copy); generic=True forces the table-driven kernel
+    pair = PairANNPGPU(ntypes=len(elems), variant=(capi.VARIANT_NI | capi.VARIANT_FLAG_GENERIC) if generic else None)
     pair.settings([])
     pair.coeff(["*", "*", pot_file] + list(elems))
     pair.init_style()
@@ -34,10 +35,11 @@ def make_anna(pot_file, elems=("Fe",)):
     return pair
 
 
+@pytest.mark.parametrize("generic", [False, True], ids=["fast", "generic"])
 @pytest.mark.parametrize("name", util.NI_CASES)
-def test_ni_golden_case(name, ni_pot_file):
+def test_ni_golden_case(name, generic, ni_pot_file):
     cfg, elems, ref = util.load_case(name, "annp_ni")
-    pair = make_ni(ni_pot_file, elems)
+    pair = make_ni(ni_pot_file, elems, generic)
     f = pair.compute(3, 1 + 4, cfg, ago=0)
     assert np.abs(pair.eatom - ref["eatom"]).max() <= 1e-10
     assert abs(pair.eng_vdwl - ref["eng_vdwl"]) <= 1e-9
