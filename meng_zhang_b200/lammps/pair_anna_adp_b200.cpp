@@ -1,0 +1,173 @@
+/* ----------------------------------------------------------------------
+   pair_style anna_adp/gpu on libannp_b200.so -- host side inside LAMMPS.
+
+   Mirrors PairANNAADPGPU of the reference (anna-gpu-lammps/bcc_fe/src/pair_anna_adp_gpu.cpp):
+     constructor 66-71, destructor 76-78, memory_usage 81-84, compute 89-157, init_style 162-260.
+   Differences, all on purpose:
+     * anna_adp_gpu_init / _compute / _compute_force / _clear / _bytes become anna_b200_init and the shared
+       annp_b200_* entry points of include/annp_b200.h
+     * newton pair ON and no forward communication of rho / mu / lambda / d2 / q2: the numbers follow the reference
+       CPU style, which centres everything on the local atom (see the header)
+     * forces / energies are ADDED to LAMMPS' arrays; no `fix gpu` / `package gpu`; no CPU fallback
+------------------------------------------------------------------------- */
+
+#include "pair_anna_adp_b200.h"
+
+#include "annp_b200.h"
+
+#include "atom.h"
+#include "comm.h"
+#include "error.h"
+#include "force.h"
+#include "memory.h"
+#include "neigh_list.h"
+#include "neigh_request.h"
+#include "neighbor.h"
+#include "suffix.h"
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace LAMMPS_NS;
+
+/* ---------------------------------------------------------------------- */
+
+PairANNAADPB200::PairANNAADPB200(LAMMPS *lmp) :
+    PairANNA_ADP(lmp), handle(nullptr), nmax_buf(0), fbuf(nullptr), ebuf(nullptr), vbuf(nullptr)
+{
+  respa_enable = 0;
+  suffix_flag |= Suffix::GPU;
+  comm_forward = 0;      // the CPU base class reserves one slot it never uses; nothing is forwarded here
+}
+
+/* ---------------------------------------------------------------------- */
+
+PairANNAADPB200::~PairANNAADPB200()
+{
+  annp_b200_clear(handle);
+  handle = nullptr;
+  free(fbuf);
+  free(ebuf);
+  free(vbuf);
+}
+
+/* ---------------------------------------------------------------------- */
+
+double PairANNAADPB200::memory_usage()
+{
+  double bytes = Pair::memory_usage();
+  bytes += (double) nmax_buf * 10 * sizeof(double);
+  return bytes + annp_b200_bytes(handle);
+}
+
+/* ---------------------------------------------------------------------- */
+
+void PairANNAADPB200::grow_buffers(int nall, int want_e, int want_v)
+{
+  if (nall > nmax_buf) {
+    nmax_buf = nall + nall / 8 + 16;
+    free(fbuf); free(ebuf); free(vbuf);
+    fbuf = (double *) malloc(sizeof(double) * 3 * (size_t) nmax_buf);
+    ebuf = vbuf = nullptr;
+  }
+  if (want_e && !ebuf) ebuf = (double *) malloc(sizeof(double) * (size_t) nmax_buf);
+  if (want_v && !vbuf) vbuf = (double *) malloc(sizeof(double) * 6 * (size_t) nmax_buf);
+  if (!fbuf || (want_e && !ebuf) || (want_v && !vbuf)) error->one(FLERR, "Out of host memory in pair anna_adp/gpu");
+}
+
+/* ----------------------------------------------------------------------
+   compute force and energy   (reference: pair_anna_adp_gpu.cpp:89-157, one library call instead of two phases)
+------------------------------------------------------------------------- */
+
+void PairANNAADPB200::compute(int eflag, int vflag)
+{
+  ev_init(eflag, vflag);
+  const int nlocal = atom->nlocal, nghost = atom->nghost, nall = nlocal + nghost;
+  double **f = atom->f;
+  int rc;
+
+  if (neighbor->ago == 0) {
+    rc = annp_b200_neigh(handle, list->inum, nall, list->ilist, list->numneigh, list->firstneigh);
+    if (rc == ANNP_B200_ENOMEM) error->one(FLERR, "Insufficient memory on accelerator");
+    if (rc) error->one(FLERR, std::string("anna_adp/gpu: ") + annp_b200_last_error(handle));
+  }
+  if (nall == 0) return;
+  grow_buffers(nall, eflag_atom, vflag_atom);
+
+  double eng = 0.0, vir[6] = {0, 0, 0, 0, 0, 0};
+  const int want_pair_virial = vflag_global && !vflag_fdotr;
+  rc = annp_b200_compute(handle, nlocal, nghost, atom->x[0], atom->type, eflag_either, vflag_either || vflag_fdotr,
+                         fbuf, eflag_global ? &eng : nullptr, eflag_atom ? ebuf : nullptr,
+                         want_pair_virial ? vir : nullptr, vflag_atom ? vbuf : nullptr);
+  if (rc == ANNP_B200_ENOMEM) error->one(FLERR, "Insufficient memory on accelerator");
+  if (rc) error->one(FLERR, std::string("anna_adp/gpu: ") + annp_b200_last_error(handle));
+
+  double *f0 = f[0];
+  for (int i = 0; i < 3 * nall; i++) f0[i] += fbuf[i];
+  if (eflag_global) eng_vdwl += eng;
+  if (eflag_atom) for (int i = 0; i < nall; i++) eatom[i] += ebuf[i];
+  if (want_pair_virial) for (int k = 0; k < 6; k++) virial[k] += vir[k];
+  if (vflag_atom)
+    for (int i = 0; i < nall; i++) for (int k = 0; k < 6; k++) vatom[i][k] += vbuf[6 * (size_t) i + k];
+
+  if (vflag_fdotr) virial_fdotr_compute();
+}
+
+/* ----------------------------------------------------------------------
+   init specific to this pair style   (reference: pair_anna_adp_gpu.cpp:162-260)
+------------------------------------------------------------------------- */
+
+void PairANNAADPB200::init_style()
+{
+  if (atom->tag_enable == 0) error->all(FLERR, "Pair style anna_adp/gpu requires atom IDs");
+  if (force->newton_pair == 0) error->all(FLERR, "Pair style anna_adp/gpu (B200) requires newton pair on");
+
+  const ANNAPARA &p = params[0];
+  const int ntl = p.ntl, nnod = p.nnod, nsf = p.nsf, nout = p.nout, nelements = p.nelements, ntypes = atom->ntypes;
+  if (ntl - 1 > ANNP_B200_MAX_LAYERS) error->all(FLERR, "anna_adp/gpu: too many network layers");
+
+  for (int i = 1; i <= ntypes; i++)
+    for (int j = i; j <= ntypes; j++) {
+      double cut = 0.0;
+      if (setflag[i][j] != 0 || (setflag[i][i] != 0 && setflag[j][j] != 0)) { cut = init_one(i, j); cut *= cut; }
+      cutsq[i][j] = cutsq[j][i] = cut;
+    }
+
+  // weights/biases flattened row-major per layer; the last layer has nout rows (reference lines 196-222)
+  std::vector<double> w, b;
+  for (int e = 0; e < nelements; e++)
+    for (int l = 0; l < ntl - 1; l++) {
+      const int nrow = (l == ntl - 2) ? nout : nnod, ncol = (l == 0) ? nsf : nnod;
+      for (int j = 0; j < nrow; j++)
+        for (int k = 0; k < ncol; k++) w.push_back(p.all_anna[e].weight_all[l][j][k]);
+      for (int j = 0; j < nrow; j++) b.push_back(p.all_anna[e].bias_all[l][0][j]);
+    }
+
+  std::vector<double> cs((size_t) (ntypes + 1) * (ntypes + 1), 0.0);
+  for (int i = 1; i <= ntypes; i++) for (int j = 1; j <= ntypes; j++) cs[(size_t) i * (ntypes + 1) + j] = cutsq[i][j];
+  std::vector<int> mp(ntypes + 1, 0);
+  for (int i = 1; i <= ntypes; i++) mp[i] = map[i] < 0 ? 0 : map[i];
+
+  anna_b200_params P;
+  memset(&P, 0, sizeof(P));
+  P.abi_version = ANNP_B200_ABI_VERSION;
+  P.ntypes = ntypes; P.nelements = nelements;
+  P.ntl = ntl; P.nhl = p.nhl; P.nnod = nnod; P.nout = nout; P.nsf = nsf; P.npsf = p.npsf; P.ntsf = p.ntsf; P.ngp = p.ngp;
+  P.flagsym = p.flagsym;
+  for (int l = 0; l < ntl - 1; l++) P.flagact[l] = p.flagact[l];
+  P.e_base = p.e_base; P.cut = p.cut;
+  P.cutsq = cs.data(); P.map = mp.data(); P.weights = w.data(); P.bias = b.data(); P.gparams = p.gparams;
+
+  annp_b200_clear(handle);
+  handle = nullptr;
+  const int ndev = annp_b200_device_count();
+  char msg[512] = "";
+  const int device = ndev > 0 ? comm->me % ndev : 0;      // one rank per GPU
+  const int rc = anna_b200_init(&P, device, &handle, msg, (int) sizeof(msg));
+  if (rc == ANNP_B200_ENOMEM) error->all(FLERR, "Insufficient memory on accelerator");
+  if (rc != 0) error->all(FLERR, std::string("anna_adp/gpu initialisation failed: ") + msg);
+
+  neighbor->add_request(this, NeighConst::REQ_FULL);
+}

@@ -1,0 +1,49 @@
+/* -*- c++ -*- ----------------------------------------------------------
+   pair_style anna_adp/gpu served by libannp_b200.so (NVIDIA B200, sm_100a).
+
+   Drop-in for the reference's src/pair_anna_adp_gpu.{h,cpp} (anna-gpu-lammps/bcc_fe): copy this header and
+   pair_anna_adp_b200.cpp next to the reference's own pair_anna_adp.{h,cpp} INSTEAD of pair_anna_adp_gpu.{h,cpp},
+   drop include/annp_b200.h beside them and link libannp_b200.so.  Input decks keep
+
+       pair_style  anna_adp/gpu
+       pair_coeff  * * fe_adp_potential_2310.anna Fe
+
+   but run with `newton on` (the default): the numbers follow the reference CPU style (pair_anna_adp.cpp:73-286),
+   everything is centred on the local atom and LAMMPS' reverse communication carries ghost forces home, so the 12
+   forward communications per step of the reference GPU style (pair_anna_adp_gpu.cpp:135-153) disappear.
+------------------------------------------------------------------------- */
+
+#ifdef PAIR_CLASS
+// clang-format off
+PairStyle(anna_adp/gpu, PairANNAADPB200);
+// clang-format on
+#else
+
+#ifndef LMP_PAIR_ANNA_ADP_B200_H
+#define LMP_PAIR_ANNA_ADP_B200_H
+
+#include "pair_anna_adp.h"      // the reference's CPU style: file parsing, coeff(), init_one()
+
+struct annp_b200_handle_s;
+
+namespace LAMMPS_NS {
+
+class PairANNAADPB200 : public PairANNA_ADP {
+ public:
+  PairANNAADPB200(class LAMMPS *);
+  ~PairANNAADPB200() override;
+  void compute(int, int) override;
+  void init_style() override;
+  double memory_usage() override;
+
+ protected:
+  annp_b200_handle_s *handle;
+  int nmax_buf;
+  double *fbuf, *ebuf, *vbuf;     // host staging: forces / per-atom energy / per-atom virial
+  void grow_buffers(int nall, int want_e, int want_v);
+};
+
+}    // namespace LAMMPS_NS
+
+#endif
+#endif

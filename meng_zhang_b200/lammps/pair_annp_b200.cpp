@@ -28,9 +28,58 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 using namespace LAMMPS_NS;
+
+/* ----------------------------------------------------------------------
+   The three `annp` copies of the reference share the class name PairANNP and the style name; a LAMMPS tree holds
+   ONE of them.  This file compiles against whichever pair_annp.h is installed: the Ni copy's parameter struct
+   carries sf_min / sf_max / sym_coerad / sym_coeang (ni/src/pair_annp.h), the Fe copies' carries
+   sfnor_cov / sfnor_avg (fe_v2/src/pair_annp.h).  The helpers below pick the members that exist.
+------------------------------------------------------------------------- */
+namespace {
+
+template <class P, class = void> struct is_ni_copy : std::false_type {};
+template <class P> struct is_ni_copy<P, std::void_t<decltype(std::declval<P>().sym_coerad)>> : std::true_type {};
+
+struct DescriptorArrays {
+  std::vector<double> scal, avg, corad, coang;
+  int variant = ANNP_B200_VARIANT_FE;
+};
+
+// Fe / fe_v2 copy: sfnor_scal = 1/sqrt(cov - avg^2), 0 when degenerate (pair_annp_gpu.cpp:211-220)
+template <class P> typename std::enable_if<!is_ni_copy<P>::value>::type fill_descriptor(const P &p, DescriptorArrays &d)
+{
+  const int nsf = p.nsf;
+  d.scal.resize(nsf); d.avg.resize(nsf);
+  for (int i = 0; i < nsf; i++) {
+    d.avg[i] = p.sfnor_avg[i];
+    const double t = sqrt(p.sfnor_cov[i] - d.avg[i] * d.avg[i]);
+    d.scal[i] = (t <= 1.0e-10) ? 0.0 : 1.0 / t;
+  }
+  d.variant = ANNP_B200_VARIANT_FE;
+}
+
+// Ni copy: (G - sf_min) / (sf_max - sf_min) and the Behler-Parrinello coefficient tables
+// (ni/src/pair_annp.cpp:99-101,168-170; ni/src/pair_annp_gpu.cpp:31-40 host_cofsymrad / host_cofsymang).
+// The Ni CPU style overwrites sf_max with the range on every compute() call; init_style runs before the first one,
+// so sf_max still holds the file's values here.
+template <class P> typename std::enable_if<is_ni_copy<P>::value>::type fill_descriptor(const P &p, DescriptorArrays &d)
+{
+  const int nsf = p.nsf;
+  d.scal.resize(nsf); d.avg.resize(nsf);
+  for (int i = 0; i < nsf; i++) { d.avg[i] = p.sf_min[i]; d.scal[i] = 1.0 / (p.sf_max[i] - p.sf_min[i]); }
+  d.corad.resize((size_t) p.npsf * 3);
+  d.coang.resize((size_t) p.ntsf * 4);
+  for (int m = 0; m < p.npsf; m++) for (int k = 0; k < 3; k++) d.corad[(size_t) m * 3 + k] = p.sym_coerad[m][k];
+  for (int n = 0; n < p.ntsf; n++) for (int k = 0; k < 4; k++) d.coang[(size_t) n * 4 + k] = p.sym_coeang[n][k];
+  d.variant = ANNP_B200_VARIANT_NI;
+}
+
+}    // namespace
 
 /* ---------------------------------------------------------------------- */
 
@@ -150,13 +199,9 @@ void PairANNPB200::init_style()
     }
   }
 
-  // sfnor_scal = 1/sqrt(cov - avg^2), 0 when degenerate (lines 211-220)
-  std::vector<double> scal(nsf), avg(nsf);
-  for (int i = 0; i < nsf; i++) {
-    avg[i] = p.sfnor_avg[i];
-    const double t = sqrt(p.sfnor_cov[i] - avg[i] * avg[i]);
-    scal[i] = (t <= 1.0e-10) ? 0.0 : 1.0 / t;
-  }
+  // descriptor normalisation (and, for the Ni copy, the symmetry-function coefficient tables)
+  DescriptorArrays desc;
+  fill_descriptor(p, desc);
 
   std::vector<double> cs((size_t) (ntypes + 1) * (ntypes + 1), 0.0);
   for (int i = 1; i <= ntypes; i++) for (int j = 1; j <= ntypes; j++) cs[(size_t) i * (ntypes + 1) + j] = cutsq[i][j];
@@ -171,8 +216,10 @@ void PairANNPB200::init_style()
   P.flagsym = p.flagsym;
   for (int l = 0; l < ntl - 1; l++) P.flagact[l] = p.flagact[l];
   P.e_scale = p.e_scale; P.e_shift = p.e_shift; P.e_atom = p.e_atom; P.cut = p.cut;
-  P.sfnor_scal = scal.data(); P.sfnor_avg = avg.data(); P.cutsq = cs.data(); P.map = mp.data();
+  P.sfnor_scal = desc.scal.data(); P.sfnor_avg = desc.avg.data(); P.cutsq = cs.data(); P.map = mp.data();
   P.weights = w.data(); P.bias = b.data();
+  P.variant = desc.variant;
+  if (desc.variant == ANNP_B200_VARIANT_NI) { P.sym_coerad = desc.corad.data(); P.sym_coeang = desc.coang.data(); }
 
   annp_b200_clear(handle);
   handle = nullptr;

@@ -20,10 +20,17 @@ BIN = {
     # NOT an oracle: our own LAMMPS-facing pair style (meng_zhang_b200/lammps/pair_annp_b200.cpp) linked against
     # libannp_b200.so and driven by the same shim + driver, so it is tested exactly like the reference style
     "plugin_annp_b200": os.path.join(HERE, "_ref", "plugin_annp_b200"),
+    "plugin_annp_ni_b200": os.path.join(HERE, "_ref", "plugin_annp_ni_b200"),
+    "plugin_anna_adp_b200": os.path.join(HERE, "_ref", "plugin_anna_adp_b200"),
 }
 
 
 def available(kind: str) -> bool:
+    if os.path.isfile(BIN[kind]) and not os.access(BIN[kind], os.X_OK):
+        try:                       # the snapshot that ships the binaries to the GPU box may drop the mode bits
+            os.chmod(BIN[kind], 0o755)
+        except OSError:
+            pass
     return os.path.isfile(BIN[kind]) and os.access(BIN[kind], os.X_OK)
 
 

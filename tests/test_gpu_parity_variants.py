@@ -131,3 +131,24 @@ def test_explicit_variant_overrides_and_rejects(fe_pot_file):
     pair.coeff(["*", "*", fe_pot_file, "Fe"])
     with pytest.raises(LammpsError):
         pair.init_style()
+
+
+@pytest.mark.parametrize("kind,prefix,name", [("plugin_annp_ni_b200", "annp_ni", "fcc3_perturbed"), ("plugin_annp_ni_b200", "annp_ni", "fcc3_two_types"),
+                                              ("plugin_anna_adp_b200", "anna_adp", "bcc4_perturbed"), ("plugin_anna_adp_b200", "anna_adp", "cluster_ragged"),
+                                              ("plugin_anna_adp_b200", "anna_adp", "bcc4_two_types")])
+def test_lammps_pair_styles_through_the_shim_driver(kind, prefix, name, ni_pot_file, anna_pot_file):
+    """The C++ classes LAMMPS would compile - PairANNPB200 built against the Ni copy of pair_annp.h, and
+    PairANNAADPB200 (anna_adp/gpu) - run by the driver that runs the reference's own classes."""
+    from oracle import run_ref
+    if not run_ref.available(kind):
+        pytest.skip(f"{kind} not built")
+    cfg, elems, ref = util.load_case(name, prefix)
+    pot = ni_pot_file if prefix == "annp_ni" else anna_pot_file
+    for vflag, vkey in ((1 + 4, "virial_pair"), (2, "virial_fdotr")):
+        out = run_ref.run_reference(kind, cfg, pot, elems, eflag=3, vflag=vflag)
+        assert abs(out["eng_vdwl"] - ref["eng_vdwl"]) <= 1e-12 * abs(ref["eng_vdwl"]) + 1e-9
+        assert np.abs(out["eatom"] - ref["eatom"]).max() <= 1e-9
+        assert np.abs(out["f"] - ref["f"]).max() <= 1e-9
+        assert np.abs(out["virial"] - ref[vkey]).max() <= 1e-8
+        if vflag & 4:
+            assert np.abs(out["vatom"] - ref["vatom"]).max() <= 1e-9
