@@ -194,7 +194,45 @@ def dump_kind(kind, prefix, potfile, cases_fn):
               f"fmax {np.abs(cfg.fold(r1['f'])).max():.6e} ({r1['seconds']:.1f} s)")
 
 
+def dump_structures():
+    """Atoms written by the reference's own structure generators (oracle/_ref/gen_screw, gen_stgb)."""
+    import subprocess
+    import tempfile
+    from meng_zhang_b200 import structures as S
+    gen = os.path.join(ROOT, "oracle", "_ref")
+
+    def run(prog, *args):
+        with tempfile.TemporaryDirectory() as td:
+            out = os.path.join(td, "o.txt")
+            subprocess.run([os.path.join(gen, prog), out, *map(str, args)], check=True, capture_output=True, cwd=td)
+            with open(out) as fp:
+                n = int(fp.readline())
+                box = np.array(fp.readline().split(), dtype=float)
+                arr = np.loadtxt(fp)
+            assert len(arr) == n
+            return arr, box
+
+    arr, box = run("gen_screw")
+    # the three atoms the reference asks its user for: two neighbours along x, the third on the vertex above them
+    x, b, t = S.screw_block(reference_rules=True)
+    core, cols = S.screw_core(x, b)
+    ids = []
+    for c in cols:
+        k = np.argmin(np.linalg.norm(arr[:, 2:4] - c, axis=1))
+        assert np.linalg.norm(arr[k, 2:4] - c) < 1e-5
+        ids.append(int(arr[k, 0]))
+    arr_s, _ = run("gen_screw", *ids)
+    np.savez_compressed(os.path.join(OUT, "gen_screw.npz"), x=arr[:, 2:5], type=arr[:, 1].astype(np.int32), box=box,
+                        ids=np.array(ids), core=core, x_screw=arr_s[:, 2:5])
+    arr2, box2 = run("gen_stgb")
+    np.savez_compressed(os.path.join(OUT, "gen_stgb.npz"), x=arr2[:, 2:5], type=arr2[:, 1].astype(np.int32), box=box2)
+    print("structures:", len(arr), len(arr2), ids, core)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "structures":
+        dump_structures()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ni_anna":      # only the round-1b additions
         dump_ni_anna_potentials()
         dump_kind("annp_ni", "annp_ni", NI_POT, ni_cases)
@@ -204,5 +242,6 @@ if __name__ == "__main__":
     dump_ni_anna_potentials()
     dump_kind("annp_ni", "annp_ni", NI_POT, ni_cases)
     dump_kind("anna_adp", "anna_adp", ANNA_POT, anna_cases)
+    dump_structures()
     dump_fe_st()
     dump_cases()
