@@ -274,6 +274,52 @@ int annp_b200_nve_initial(annp_b200_handle h, int nlocal, double dt, double mass
 int annp_b200_nve_final(annp_b200_handle h, int nlocal, double dt, double mass, double *d_v, const double *d_f,
                         double *d_ke, void *stream);
 
+/* ---- Nose-Hoover chains on the device: `fix nvt` / `fix npt` of the reference's decks (in.st_test:30-37) ---------------
+ * LAMMPS' FixNH operator splitting (MTK equations, tchain = pchain = 3, one sub-cycle), orthogonal box, independent
+ * x / y / z barostat coupling, metal units.  The extended variables live in device memory and are advanced by
+ * single-thread kernels, so a step never synchronises with the host.  One MD step of a rank:
+ *     annp_b200_nh_initial     chain half step + per-atom: thermostat/barostat velocity scaling, kick, box dilation,
+ *                              drift (positions and, for npt, the periodic image shifts of the halo send list)
+ *     [halo, annp_b200_compute_device with vflag = 1, reverse halo]
+ *     annp_b200_nh_final_kick  per-atom kick + barostat scaling; red12 = this rank's [m sum v(x)v (6), pair virial (6)]
+ *     [sum red12 over ranks: ncclAllReduce / torch.distributed.all_reduce; nothing to do on one rank]
+ *     annp_b200_nh_final_scale chain half step from the summed tensors + per-atom thermostat scaling
+ * annp_b200_nh_reduce + annp_b200_nh_setup initialise temperature, pressure and chain masses before the first step
+ * (FixNH::setup).  All d_* pointers are device pointers; stream is a cudaStream_t. */
+typedef struct annp_b200_nh_s *annp_b200_nh;
+typedef struct annp_b200_nh_config {
+  int tstat, pstat;              /* fix nvt: 1, 0     fix npt: 1, 1                                        */
+  double t_start, t_stop, t_damp;/* K, K, ps                                                               */
+  int p_flag[3];                 /* coupled dimensions (the deck: y only)                                  */
+  double p_start[3], p_stop[3], p_damp[3];   /* bar, bar, ps                                               */
+  int tchain, pchain, mtk;       /* LAMMPS defaults 3, 3, 1                                                */
+  double dt, mass;               /* ps, g/mol (single species)                                             */
+  double natoms_total;           /* atoms of the whole system (all ranks)                                  */
+  double tdof;                   /* temperature degrees of freedom; <= 0: 3 natoms - 3                     */
+  long long nsteps_ramp;         /* run length over which start -> stop ramps (0: constant targets)        */
+} annp_b200_nh_config;
+typedef struct annp_b200_nh_state {
+  long long step;
+  double t_current, t_target;
+  double p_current[3];           /* bar */
+  double boxlo[3], boxhi[3];
+  double omega_dot[3];
+  double ke_tensor[6], virial[6];/* eV */
+  double eta[8], eta_dot[8], etap[8], etap_dot[8];
+  double extended_energy;        /* FixNH::compute_scalar: PE + KE + this is the conserved quantity (eV)   */
+} annp_b200_nh_state;
+int annp_b200_nh_create(const annp_b200_nh_config *cfg, const double *boxlo, const double *boxhi, int device,
+                        annp_b200_nh *out, char *err, int errlen);
+void annp_b200_nh_destroy(annp_b200_nh nh);
+int annp_b200_nh_reduce(annp_b200_nh nh, int nlocal, const double *d_v, const double *d_eng_virial, double *d_red12, void *stream);
+int annp_b200_nh_setup(annp_b200_nh nh, const double *d_red12, void *stream);
+int annp_b200_nh_initial(annp_b200_nh nh, int nlocal, double *d_x, double *d_v, const double *d_f, int nsend,
+                         double *d_send_shift, void *stream);
+int annp_b200_nh_final_kick(annp_b200_nh nh, int nlocal, double *d_v, const double *d_f, const double *d_eng_virial,
+                            double *d_red12, void *stream);
+int annp_b200_nh_final_scale(annp_b200_nh nh, int nlocal, double *d_v, const double *d_red12, void *stream);
+int annp_b200_nh_get_state(annp_b200_nh nh, annp_b200_nh_state *out, void *stream);   /* synchronises the stream */
+
 /* measured FP64 FMA throughput of this device in TFLOP/s (pure DFMA loop, best of reps): the
  * denominator of the force kernel's roofline (MEASURED_PEAKS.json has no FP64 entry) */
 double annp_b200_fp64_peak_tflops(annp_b200_handle h, int reps);

@@ -72,6 +72,25 @@ class AnnaParams(C.Structure):
     ]
 
 
+class NhConfig(C.Structure):
+    _fields_ = [
+        ("tstat", C.c_int), ("pstat", C.c_int), ("t_start", C.c_double), ("t_stop", C.c_double), ("t_damp", C.c_double),
+        ("p_flag", C.c_int * 3), ("p_start", C.c_double * 3), ("p_stop", C.c_double * 3), ("p_damp", C.c_double * 3),
+        ("tchain", C.c_int), ("pchain", C.c_int), ("mtk", C.c_int), ("dt", C.c_double), ("mass", C.c_double),
+        ("natoms_total", C.c_double), ("tdof", C.c_double), ("nsteps_ramp", C.c_longlong),
+    ]
+
+
+class NhState(C.Structure):
+    _fields_ = [
+        ("step", C.c_longlong), ("t_current", C.c_double), ("t_target", C.c_double), ("p_current", C.c_double * 3),
+        ("boxlo", C.c_double * 3), ("boxhi", C.c_double * 3), ("omega_dot", C.c_double * 3),
+        ("ke_tensor", C.c_double * 6), ("virial", C.c_double * 6),
+        ("eta", C.c_double * 8), ("eta_dot", C.c_double * 8), ("etap", C.c_double * 8), ("etap_dot", C.c_double * 8),
+        ("extended_energy", C.c_double),
+    ]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("inum", C.c_int), ("nall", C.c_int), ("max_neigh_list", C.c_int), ("max_neigh_cut", C.c_int),
@@ -107,6 +126,14 @@ PROTOTYPES = {
     "annp_b200_halo_unpack_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_nve_initial": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_nve_final": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_nh_create": (C.c_int, [C.POINTER(NhConfig), c_double_p, c_double_p, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),
+    "annp_b200_nh_destroy": (None, [C.c_void_p]),
+    "annp_b200_nh_reduce": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_nh_setup": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_nh_initial": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "annp_b200_nh_final_kick": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_nh_final_scale": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_nh_get_state": (C.c_int, [C.c_void_p, C.POINTER(NhState), C.c_void_p]),
     "annp_b200_fp64_peak_tflops": (C.c_double, [C.c_void_p, C.c_int]),
     "annp_b200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "annp_b200_set_timing": (C.c_int, [C.c_void_p, C.c_int]),

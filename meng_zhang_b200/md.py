@@ -232,6 +232,112 @@ class DomainMD:
                                             C.c_void_p(self.f.data_ptr()), ke, s))
         self.nsteps += 1
 
+    # ------------------------------------------------------------------ fix nvt / fix npt (device-resident Nose-Hoover)
+    def fix_nh(self, t_start, t_stop, t_damp, p_flag=(0, 0, 0), p_start=(0.0, 0.0, 0.0), p_stop=(0.0, 0.0, 0.0),
+               p_damp=(1.0, 1.0, 1.0), tchain=3, pchain=3, nsteps_ramp=0):
+        """`fix nvt temp t_start t_stop t_damp` (p_flag all 0) or `fix npt ... x|y|z p_start p_stop p_damp`
+        (in.st_test:30-37 couples y only: p_flag=(0,1,0)).  Call after reneighbor() + compute(vflag=True)."""
+        cfg = capi.NhConfig()
+        cfg.tstat, cfg.pstat = 1, int(any(p_flag))
+        cfg.t_start, cfg.t_stop, cfg.t_damp = t_start, t_stop, t_damp
+        for d in range(3):
+            cfg.p_flag[d], cfg.p_start[d], cfg.p_stop[d], cfg.p_damp[d] = int(p_flag[d]), p_start[d], p_stop[d], p_damp[d]
+        cfg.tchain, cfg.pchain, cfg.mtk = tchain, pchain, 1
+        cfg.dt, cfg.mass = self.dt, self.mass
+        ntot = torch.tensor([float(self.nlocal)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ntot, group=self.group)
+        cfg.natoms_total = float(ntot)
+        cfg.tdof = 0.0
+        cfg.nsteps_ramp = nsteps_ramp
+        lo, hi = np.zeros(3), self.box.astype(np.float64).copy()
+        err = C.create_string_buffer(256)
+        h = C.c_void_p(None)
+        rc = self.L.annp_b200_nh_create(C.byref(cfg), lo.ctypes.data_as(capi.c_double_p), hi.ctypes.data_as(capi.c_double_p),
+                                        self.dev.index if self.dev.index is not None else -1, C.byref(h), err, 256)
+        if rc != 0:
+            raise capi.AnnpError(rc, err.value.decode())
+        self.nh = h
+        self.nh_pstat = bool(cfg.pstat)
+        self.red12 = torch.zeros(12, dtype=torch.float64, device=self.dev)
+        if self.x is None:
+            self.reneighbor()
+        self.compute(eflag=True, vflag=True)
+        s = self._stream()
+        self._nh_ck(self.L.annp_b200_nh_reduce(self.nh, self.nlocal, C.c_void_p(self.v.data_ptr()), C.c_void_p(self.engvir.data_ptr()),
+                                               C.c_void_p(self.red12.data_ptr()), s))
+        self._allreduce_red12()
+        self._nh_ck(self.L.annp_b200_nh_setup(self.nh, C.c_void_p(self.red12.data_ptr()), s))
+
+    def _nh_ck(self, rc):
+        if rc != 0:
+            raise capi.AnnpError(rc, "Nose-Hoover integrator call failed")
+
+    def _allreduce_red12(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.red12, group=self.group)
+
+    def step_nh(self, eflag=False):
+        """One step of FixNH::initial_integrate, force, FixNH::final_integrate."""
+        s = self._stream()
+        shift = C.c_void_p(self.send_shift.data_ptr()) if self.nsend > 0 else None
+        self._nh_ck(self.L.annp_b200_nh_initial(self.nh, self.nlocal, C.c_void_p(self.x.data_ptr()), C.c_void_p(self.v.data_ptr()),
+                                                C.c_void_p(self.f.data_ptr()), self.nsend, shift, s))
+        self.compute(eflag=eflag, vflag=True)
+        self._nh_ck(self.L.annp_b200_nh_final_kick(self.nh, self.nlocal, C.c_void_p(self.v.data_ptr()), C.c_void_p(self.f.data_ptr()),
+                                                   C.c_void_p(self.engvir.data_ptr()), C.c_void_p(self.red12.data_ptr()), s))
+        self._allreduce_red12()
+        self._nh_ck(self.L.annp_b200_nh_final_scale(self.nh, self.nlocal, C.c_void_p(self.v.data_ptr()), C.c_void_p(self.red12.data_ptr()), s))
+        self.nsteps += 1
+
+    def nh_state(self):
+        st = capi.NhState()
+        self._nh_ck(self.L.annp_b200_nh_get_state(self.nh, C.byref(st), self._stream()))
+        return st
+
+    def sync_box_from_nh(self):
+        """After npt steps the box lives in the thermostat state: refresh the host copy (needed to re-neighbour)."""
+        st = self.nh_state()
+        lo, hi = np.array(st.boxlo[:]), np.array(st.boxhi[:])
+        self.box_origin = lo
+        self.box = hi - lo
+        self.lo = lo + np.array([self.box[d] * self.coords[d] / self.grid[d] for d in range(3)])
+        self.hi = lo + np.array([self.box[d] * (self.coords[d] + 1) / self.grid[d] for d in range(3)])
+        return st
+
+    def run_nh(self, nsteps: int, check_every: int = 5, thermo_every: int = 0):
+        """`run nsteps` under fix nvt / npt with the deck's re-neighbouring rule.  Returns
+        [(step, pe, ke, extended_energy, T, (pxx, pyy, pzz), box[3])] at the thermo steps."""
+        x_ref = self.x[: self.nlocal].clone()
+        out, self.rebuilds = [], 0
+        for n in range(1, nsteps + 1):
+            want = thermo_every > 0 and (n % thermo_every == 0 or n == nsteps)
+            if check_every > 0 and n % check_every == 0:
+                # the deck's criterion on the displacement since the last build (box dilation included)
+                moved = (self.x[: self.nlocal] - x_ref).square().sum(dim=1).max()
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(moved, op=dist.ReduceOp.MAX, group=self.group)
+                if float(moved) > (0.5 * self.skin) ** 2:
+                    if self.nh_pstat:
+                        self.sync_box_from_nh()
+                    self.reneighbor()
+                    x_ref = self.x[: self.nlocal].clone()
+                    self.rebuilds += 1
+            self.step_nh(eflag=want)
+            if want:
+                st = self.nh_state()
+                pe = self.engvir[:1].clone()
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(pe, group=self.group)
+                ke = 0.5 * (st.ke_tensor[0] + st.ke_tensor[1] + st.ke_tensor[2])
+                out.append((self.nsteps, float(pe), ke, st.extended_energy, st.t_current, tuple(st.p_current[:]),
+                            tuple(st.boxhi[d] - st.boxlo[d] for d in range(3))))
+        return out
+
     def thermo(self):
         """(pe, ke) of the whole system in eV after a step(eflag=True)."""
         t = torch.stack([self.engvir[0], self.ke[0]])

@@ -1,0 +1,105 @@
+"""Device-resident Nose-Hoover integrators (csrc/annp_nh.cu: fix nvt / fix npt of the reference decks).  -m gpu.
+
+LAMMPS is not in this image, so the integrator is pinned two ways:
+  * step by step against tests/nh_host.py, a numpy twin written line by line after FixNH's published algorithm, fed with
+    the forces and virial the GPU produced (positions / velocities / box / chain variables to 1e-11)
+  * physically: the extended energy PE + KE + E_chain is conserved, the temperature settles at the target, and under
+    `npt y 0 0 1` (in.st_test:30-37) the coupled stress relaxes to the target while the uncoupled box edges stay put.
+"""
+import numpy as np
+import pytest
+import torch
+
+import nh_host
+import util
+from meng_zhang_b200 import lattice as L
+from meng_zhang_b200.md import DomainMD
+from meng_zhang_b200.pair import PairANNPGPU
+
+pytestmark = pytest.mark.gpu
+MASS, DT = 55.845, 0.001
+
+
+def make_md(fe_pot_file, cells, seed=7):
+    pair = PairANNPGPU(ntypes=1)
+    pair.settings([])
+    pair.coeff(["*", "*", fe_pot_file, "Fe"])
+    pair.init_style()
+    x, box = L.bcc(cells, cells, cells)
+    md = DomainMD(pair, x, box, mass=MASS, dt=DT)
+    md.set_velocities(300.0, seed)
+    md.reneighbor()
+    return pair, md
+
+
+@pytest.mark.parametrize("p_flag", [(0, 0, 0), (0, 1, 0), (1, 1, 1)], ids=["nvt", "npt_y", "npt_xyz"])
+def test_step_by_step_against_the_host_twin(p_flag, fe_pot_file):
+    pair, md = make_md(fe_pot_file, 4)
+    kw = dict(p_flag=p_flag, p_start=(0.0, 0.0, 0.0), p_stop=(0.0, 0.0, 0.0), p_damp=(1.0, 1.0, 1.0))
+    md.fix_nh(300.0, 300.0, 0.1, **kw)
+    n = md.nlocal
+    x_h, v_h = md.x[:n].cpu().numpy().copy(), md.v.cpu().numpy().copy()
+    f_prev = md.f[:n].cpu().numpy().copy()
+    twin = nh_host.HostNH(n, md.box, DT, MASS, 300.0, 300.0, 0.1, **kw)
+    twin.setup(v_h, md.engvir[1:7].cpu().numpy())
+    st = md.nh_state()
+    assert abs(st.t_current - twin.t_current) < 1e-10
+    for step in range(30):
+        md.step_nh(eflag=True)
+        x_h, v_h = twin.initial(x_h, v_h, f_prev)
+        f_dev = md.f[:n].cpu().numpy().copy()
+        v_h = twin.final(v_h, f_dev, md.engvir[1:7].cpu().numpy())
+        f_prev = f_dev
+        st = md.nh_state()
+        assert np.abs(md.x[:n].cpu().numpy() - x_h).max() < 1e-11, step
+        assert np.abs(md.v.cpu().numpy() - v_h).max() < 1e-11, step
+        assert np.abs(np.array(st.boxhi[:]) - twin.boxhi).max() < 1e-11 and np.abs(np.array(st.boxlo[:]) - twin.boxlo).max() < 1e-11
+        assert abs(st.t_current - twin.t_current) < 1e-9
+        assert np.abs(np.array(st.eta_dot[:3]) - twin.eta_dot[:3]).max() < 1e-12
+        assert abs(st.extended_energy - twin.extended_energy()) < 1e-10
+        if any(p_flag):
+            assert np.abs(np.array(st.omega_dot[:]) - twin.omega_dot).max() < 1e-13
+            assert np.abs(np.array(st.p_current[:]) - twin.p_current).max() < 1e-5        # bar
+    # ghosts follow the dilating box: periodic images stay exactly one (current) box edge away
+    if any(p_flag):
+        box_now = np.array(st.boxhi[:]) - np.array(st.boxlo[:])
+        sh = md.send_shift.cpu().numpy()
+        k = np.round(sh / box_now)
+        assert np.abs(sh - k * box_now).max() < 1e-9 and np.abs(k).max() == 1
+    pair.clear()
+
+
+def test_nvt_controls_temperature_and_conserves_extended_energy(fe_pot_file):
+    pair, md = make_md(fe_pot_file, 10, seed=4928459)           # BASELINE config 1 geometry, config 2's thermostat
+    md.fix_nh(300.0, 300.0, 0.1)
+    out = md.run_nh(3000, thermo_every=20)
+    n = md.nlocal
+    cons = np.array([(pe + ke + ext) / n for _, pe, ke, ext, *_ in out])
+    temp = np.array([o[4] for o in out])
+    assert np.abs(cons - cons[0]).max() < 2e-5                  # eV/atom over 3 ps (NVE drift of the same system: 1.6e-5)
+    late = temp[len(temp) // 2:]
+    assert abs(late.mean() - 300.0) < 10.0                      # 2 000 atoms: sigma_T ~ 300 sqrt(2/6000) = 5.5 K
+    assert 2.0 < late.std() < 25.0                              # canonical sigma 5.5 K plus the chain's ringing at t_damp = 0.1 ps
+    pair.clear()
+
+
+def test_npt_y_relaxes_the_coupled_stress_only(fe_pot_file):
+    pair, md = make_md(fe_pot_file, 8, seed=11)
+    box0 = md.box.copy()
+    md.fix_nh(300.0, 300.0, 0.1, p_flag=(0, 1, 0), p_start=(0, 0, 0), p_stop=(0, 0, 0), p_damp=(1.0, 1.0, 1.0))
+    p0 = np.array(md.nh_state().p_current[:])
+    out = md.run_nh(4000, thermo_every=20)
+    n = md.nlocal
+    cons = np.array([(pe + ke + ext) / n for _, pe, ke, ext, *_ in out])
+    assert np.abs(cons - cons[0]).max() < 5e-5
+    boxes = np.array([o[6] for o in out])
+    pyy = np.array([o[5][1] for o in out])
+    assert np.all(boxes[:, 0] == box0[0]) and np.all(boxes[:, 2] == box0[2])     # uncoupled edges never move
+    assert np.ptp(boxes[:, 1]) > 1e-3                                            # the coupled one breathes
+    # at a = 2.8553 A this potential is under ~ -4e4 bar of tension (the reference's own log: -40 423 bar at step 0,
+    # log_relaxing_new.lammps:120); the barostat brings <p_yy> to the target by contracting the coupled edge
+    assert p0[1] < -2.0e4
+    late = pyy[len(pyy) // 2:]
+    assert abs(late.mean()) < 0.25 * abs(p0[1]) + 1500.0
+    assert boxes[-1, 1] < box0[1]
+    pair.clear()
