@@ -224,6 +224,9 @@ def run_ours(args):
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline_reference(sample_cells=10, repeats=1)
+    published = None
+    if rank == 0 and world == 1 and not args.no_published_deck:
+        published = run_published_deck(pot_file, dev)
 
     if rank == 0:
         out = {
@@ -248,10 +251,51 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu_base,
+            "published_deck": published,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_published_deck(pot_file, device, steps=1000):
+    """The one run the reference publishes a speed for: its own 152 880-atom bcc-Fe slab fe_st.dat,
+    `boundary m p m`, `fix npt temp 300 300 0.1 y 0 0 1`, dt 1 fs, thermo every step, 1 000 steps - 1 789.44 s on the
+    authors' 2 GPUs = 8.55e4 atom-steps/s (log_relaxing_new.lammps:1168-1176).  Same deck here on ONE B200, device
+    resident (the deck's 1-iteration minimisation is skipped; positions are the data file's)."""
+    import torch
+    import util
+    from meng_zhang_b200.md import DomainMD
+    from meng_zhang_b200.pair import PairANNPGPU
+    z = np.load(os.path.join(util.GOLDEN, "fe_st.npz"))
+    box = z["box"]
+    x = z["x"] - box[:, 0]
+    pair = PairANNPGPU(ntypes=1, device=device.index, skin=SKIN)
+    pair.settings([])
+    pair.coeff(["*", "*", pot_file, "Fe"])
+    pair.init_style()
+    md = DomainMD(pair, x, box[:, 1] - box[:, 0], device=device, skin=SKIN, mass=55.845, dt=0.001, periodic=(False, True, False))
+    md.set_velocities(300.0, 4928459)
+    md.reneighbor()
+    md.fix_nh(300.0, 300.0, 0.1, p_flag=(0, 1, 0), p_start=(0.0, 0.0, 0.0), p_stop=(0.0, 0.0, 0.0), p_damp=(1.0, 1.0, 1.0))
+    md.run_nh(20, thermo_every=1)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = md.run_nh(steps, thermo_every=1)
+    e1.record()
+    torch.cuda.synchronize(device)
+    secs = e0.elapsed_time(e1) * 1e-3
+    natoms = len(x)
+    ref_value = 152880 * 1000 / 1789.44
+    res = {"deck": "fe_st.dat 152 880 atoms, boundary m p m, fix npt temp 300 300 0.1 y 0 0 1, thermo 1, 1000 steps (zip:in.st_test)",
+           "steps": steps, "seconds": secs, "atom_steps_per_s": natoms * steps / secs, "ns_per_day": 86400.0 * steps / secs * 1e-6,
+           "published_atom_steps_per_s": ref_value, "published_setup": "2 MPI ranks x 2 GPUs (RTX A5000 class), LAMMPS 29Sep2021, annp/gpu fe_v2",
+           "ratio_vs_published": natoms * steps / secs / ref_value, "rebuilds": md.rebuilds,
+           "T_final": out[-1][4], "pyy_final_bar": out[-1][5][1], "ly_final": out[-1][6][1],
+           "published_step1000": "see zip:log_relaxing_new.lammps (T, Ly, Pyy columns)"}
+    pair.clear()
+    return res
 
 
 def split_config(cfg, nparts):
@@ -353,6 +397,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-cells", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-published-deck", action="store_true", help="skip the reference's own published deck (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

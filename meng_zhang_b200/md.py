@@ -52,8 +52,9 @@ def coords_rank(c, grid):
     return (c[0] % px) + (c[1] % py) * px + (c[2] % pz) * px * py
 
 
-def build_send_lists(x_local: np.ndarray, lo, hi, box, grid, coords, cutghost: float):
-    """Send entries for the 26 directions, grouped by destination rank.
+def build_send_lists(x_local: np.ndarray, lo, hi, box, grid, coords, cutghost: float, periodic=(True, True, True)):
+    """Send entries for the 26 directions, grouped by destination rank.  A direction that leaves the box through a
+    non-periodic face (`boundary m`/`f`/`s` of the decks: free surface) has no receiver and is skipped.
 
     Returns (index[int32 nsend], shift[nsend,3], send_counts[nranks]) with entries ordered by
     destination rank and, inside one destination, by direction."""
@@ -67,6 +68,8 @@ def build_send_lists(x_local: np.ndarray, lo, hi, box, grid, coords, cutghost: f
             continue
         mask = np.ones(len(x_local), dtype=bool)
         shift = np.zeros(3)
+        if any(s[d] != 0 and not periodic[d] and not (0 <= coords[d] + s[d] < grid[d]) for d in range(3)):
+            continue
         for d in range(3):
             if s[d] == 1:
                 mask &= x_local[:, d] >= hi[d] - cutghost
@@ -96,7 +99,10 @@ class DomainMD:
     """One rank's sub-domain, device resident.  `pair` is an initialised PairANNPGPU."""
 
     def __init__(self, pair, x_local, box, grid=(1, 1, 1), rank=0, device=None, type_local=None,
-                 skin=2.0, mass=55.845, dt=0.001, group=None):
+                 skin=2.0, mass=55.845, dt=0.001, group=None, periodic=(True, True, True), frozen_local=None):
+        """periodic: per-axis `boundary p` (True) or free surface (False).  frozen_local: boolean mask of atoms held
+        fixed (force and velocity zeroed every step: `fix setforce 0 0 0` on the rim of the dislocation cylinder)."""
+        self.periodic = tuple(bool(p) for p in periodic)
         self.pair = pair
         self.L = capi.lib()
         self.h = pair.handle
@@ -120,6 +126,9 @@ class DomainMD:
         self.ke = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.x = self.f = self.type = None
         self.nsteps = 0
+        self.frozen_idx = None
+        if frozen_local is not None and np.any(frozen_local):
+            self.frozen_idx = torch.as_tensor(np.nonzero(np.asarray(frozen_local))[0], dtype=torch.int64, device=self.dev)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -137,6 +146,8 @@ class DomainMD:
         v = torch.randn((self.nlocal, 3), generator=g, dtype=torch.float64) * sigma
         v -= v.mean(dim=0, keepdim=True)
         self.v = v.to(self.dev)
+        if self.frozen_idx is not None:
+            self.v.index_fill_(0, self.frozen_idx, 0.0)
 
     # ------------------------------------------------------------------ re-neighbouring (ago == 0)
     def reneighbor(self):
@@ -144,7 +155,7 @@ class DomainMD:
         xl = (self.x[: self.nlocal] if self.x is not None else self._x_local0)
         xl_host = xl.cpu().numpy()
         cutghost = self.cut + self.skin
-        idx, shift, send_counts = build_send_lists(xl_host, self.lo, self.hi, self.box, self.grid, self.coords, cutghost)
+        idx, shift, send_counts = build_send_lists(xl_host, self.lo, self.hi, self.box, self.grid, self.coords, cutghost, self.periodic)
         self.send_counts = [int(c) for c in send_counts]
         if self.world > 1:
             import torch.distributed as dist
@@ -220,6 +231,8 @@ class DomainMD:
                                                  C.c_void_p(self.type.data_ptr()), int(eflag), int(vflag),
                                                  C.c_void_p(self.f.data_ptr()), None, ev, None, self._stream()))
         self.reverse_comm()
+        if self.frozen_idx is not None:
+            self.f.index_fill_(0, self.frozen_idx, 0.0)
 
     def step(self, eflag=False):
         """One velocity-Verlet step (FixNVE::initial_integrate, force, final_integrate)."""
