@@ -169,3 +169,16 @@ def test_ni_forces_are_not_the_exact_energy_gradient_but_close(ni_pot):
         fd = -(e[0] - e[1]) / (2 * h) * 51.422515 / 1.889726     # network units per Angstrom -> CFFORCE per Bohr^-1
         worst = max(worst, abs(fd - base["f"][atom, k]))
     assert 1e-3 < worst < 5e-2      # ~1e-2 eV/A: a property of the reference's formula, not rounding
+
+
+def test_ni_forces_depend_on_neighbour_row_order_energies_do_not(ni_pot):
+    """Reference property kept by the oracle and the CUDA path: the first/second member of a pair is decided by the
+    position in the neighbour row and enters the Ni copy's derivative asymmetrically (ni/src/pair_annp.cpp:734-735),
+    so re-ordering the rows changes the forces at the 1e-2 eV/A level while G and E stay put (to rounding)."""
+    x, box = L.fcc(3, 3, 3)
+    xp = L.perturb(x, 0.05, 12345)
+    a = restatement.compute_ni(ni_pot, L.build_config(xp, box, 6.5), dump_G=True)
+    b = restatement.compute_ni(ni_pot, L.build_config(xp, box, 6.5, shuffle_rows=3), dump_G=True)
+    assert np.abs(a["G"] - b["G"]).max() < 1e-12 and abs(a["eng_vdwl"] - b["eng_vdwl"]) < 1e-10
+    d = np.abs(a["f"] - b["f"]).max()
+    assert 1e-4 < d < 5e-2
