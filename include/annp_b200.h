@@ -78,6 +78,8 @@ typedef struct annp_b200_handle_s *annp_b200_handle;
 /* or'ed into params.variant: run the generic Behler-Parrinello kernel even when the coefficient table has the product
  * structure the fast kernel is specialised for (used by the tests to keep both kernels covered) */
 #define ANNP_B200_VARIANT_FLAG_GENERIC 0x100
+/* or'ed into params.variant: use the lane-per-neighbour fast kernel even when the tile fits the pair-compaction kernel */
+#define ANNP_B200_VARIANT_FLAG_NOPAIR 0x200
 
 /*
  * Flat parameter block == the argument list of annp_gpu_init (src/pair_annp_gpu.cpp:31-39).

@@ -18,6 +18,7 @@ ABI_VERSION = 2
 VARIANT_FE, VARIANT_NI, VARIANT_ANNA_ADP = 0, 1, 2
 MAX_GPARAMS = 32
 VARIANT_FLAG_GENERIC = 0x100
+VARIANT_FLAG_NOPAIR = 0x200
 
 OK, ENOMEM, ENODEVICE, EINVAL, ECUDA, ESTATE, EOVERFLOW, EIO = 0, -3, -4, -20, -21, -22, -23, -24
 

@@ -461,6 +461,7 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
     }
     hp.ang_rc = p->sym_coeang[3];                          // ni/src/pair_annp.cpp:731
     hp.bp_layout = (p->variant & ANNP_B200_VARIANT_FLAG_GENERIC) ? 0 : annp_bp_layout(hp);
+    if (hp.bp_layout == 1 && (p->variant & ANNP_B200_VARIANT_FLAG_NOPAIR)) hp.bp_layout = 2;
   }
   rc = upload_params(h, p->weights, p->bias, !ni, err, errlen);
   if (rc) { annp_b200_clear(h); return rc; }

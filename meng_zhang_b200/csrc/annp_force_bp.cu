@@ -588,6 +588,324 @@ __global__ void __launch_bounds__(kWarps * 32, 3) annp_bp_fast_kernel(const Forc
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// v2 of the fast path, used when the neighbour tile holds <= 32 atoms (Ni: 18-22 inside 3.9 A): PAIR COMPACTION.
+// Only ~40 % of the N(N-1)/2 neighbour pairs have r_jk inside the cutoff, and with "lane <-> neighbour" loops 18 of
+// 32 lanes do 17 serial pair evaluations each.  Here the contributing pairs are found first (folded-triangle sweep,
+// ballot compaction into a shared list), then forward and backward passes run with lane <-> compacted pair (2-3 full
+// iterations instead of 17+9 ragged ones).  The backward pass writes the gradient of both members of a pair into a
+// per-pair slot; each neighbour then adds its slots in ascending partner order -> fixed summation order, no atomics.
+constexpr int kBpPairCap = 64;       // gradient slots per chunk (6 doubles each); more pairs are processed in chunks
+
+template <int NE, int NZ>
+__global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const ForceArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = NE * NZ * 2;
+  constexpr int C = 32;                                   // tile size this kernel is launched for
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const DevParams &P = *a.prm;
+  const int nsf = P.nsf, npsf = P.npsf, nnod = P.nnod, nl = P.nlayers;
+  const int wtot = P.nelements * P.w_per_elem, btot = P.nelements * P.b_per_elem;
+
+  double *sW = reinterpret_cast<double *>(smem_raw);
+  double *sBias = sW + wtot;
+  double *blk_end = sBias + btot;
+  for (int t = threadIdx.x; t < wtot; t += blockDim.x) sW[t] = P.weights[t];
+  for (int t = threadIdx.x; t < btot; t += blockDim.x) sBias[t] = P.bias[t];
+  // per warp: geometry [C], gradient slots [cap][6], G/dE/c [3 nsf], MLP scratch, pair list [C(C-1)/2] u32, slot table [C][C] u16, spos [C]
+  const size_t per_warp_doubles = (size_t) 6 * C + (size_t) 6 * kBpPairCap + 3 * nsf + (size_t) 2 * nl * nnod + 2 * nnod;
+  size_t warp_bytes = per_warp_doubles * sizeof(double) + (size_t) (C * (C - 1) / 2) * sizeof(unsigned) + (size_t) C * C * sizeof(unsigned short) + (size_t) C * sizeof(int);
+  warp_bytes = (warp_bytes + 15) & ~(size_t) 15;
+  const size_t blk_bytes = ((size_t) ((unsigned char *) blk_end - smem_raw) + 15) & ~(size_t) 15;
+  unsigned char *wbase = smem_raw + blk_bytes + (size_t) warp * warp_bytes;
+  BpGeom *sN = reinterpret_cast<BpGeom *>(wbase);
+  double *sT = reinterpret_cast<double *>(sN + C);                 // [kBpPairCap][6]
+  double *sG = sT + 6 * kBpPairCap;
+  double *sdE = sG + nsf;
+  double *sCn = sdE + nsf;
+  double *sH = sCn + nsf;
+  double *sHd = sH + nl * nnod;
+  double *sDel = sHd + nl * nnod;
+  unsigned *sPair = reinterpret_cast<unsigned *>(sDel + 2 * nnod);  // a | b << 16
+  unsigned short *sSlot = reinterpret_cast<unsigned short *>(sPair + C * (C - 1) / 2);   // [C][C] pair index or 0xffff
+  int *spos = reinterpret_cast<int *>(sSlot + C * C);
+  __syncthreads();
+
+  const double Rc_rad = P.rad_rc, Rc = P.ang_rc, rcinv = 1.0 / Rc;
+  const double Rc_max = fmax(Rc_rad, Rc);
+  double eta[NE];
+#pragma unroll
+  for (int e = 0; e < NE; e++) eta[e] = P.ang_eta[e * NZ * 2];
+
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(&a.cnt->work, 1ull);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= (unsigned long long) a.inum) break;
+    const int ii = (int) item;
+    const int i = a.ilist[ii];
+    const double4 xi = a.xq[i];
+    const int ti = (int) xi.w;
+    const long long p0 = a.row_off[ii];
+    const int L = (int) (a.row_off[ii + 1] - p0);
+
+    // ---- 1. filter (list order kept).  Four row chunks per trip: the index loads, then the position gathers, are
+    // issued back to back so their L2 latencies overlap (the kernel is latency-, not throughput-bound)
+    int N = 0;
+    for (int base = 0; base < L; base += 128) {
+      int jv[4];
+      double4 xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = base + 32 * u + lane;
+        jv[u] = (q < L) ? (a.nbr[p0 + q] & ANNP_NEIGHMASK) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) xv[u] = (jv[u] >= 0) ? a.xq[jv[u]] : make_double4(0.0, 0.0, 0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = base + 32 * u + lane;
+        if (base + 32 * u >= L) break;
+        const bool valid = jv[u] >= 0;
+        const double dx = xi.x - xv[u].x, dy = xi.y - xv[u].y, dz = xi.z - xv[u].z;
+        const double r = sqrt(dx * dx + dy * dy + dz * dz);
+        const bool in = valid && (r * CFLENGTH < Rc_max);
+        const unsigned mask = __ballot_sync(0xffffffffu, in);
+        const int slot = N + __popc(mask & ((1u << lane) - 1u));
+        if (in && slot < C) {
+          BpGeom g;
+          const double rinv = 1.0 / r;
+          g.ux = dx * rinv; g.uy = dy * rinv; g.uz = dz * rinv; g.r = r;
+          double sn, cs;
+          sincospi(r * CFLENGTH * rcinv, &sn, &cs);
+          g.fc = 0.5 * (cs + 1.0);
+          g.dfc = -0.5 * kPi * rcinv * sn;
+          sN[slot] = g;
+          spos[slot] = q;
+        } else if (valid) {
+          a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+          if (a.vpair) {
+            double *vp = a.vpair + (size_t) (p0 + q) * 6;
+#pragma unroll
+            for (int k = 0; k < 6; k++) vp[k] = 0.0;
+          }
+        }
+        N += __popc(mask);
+      }
+    }
+    if (lane == 0) {
+      atomicMax(&a.cnt->max_neigh, N);
+      atomicAdd(&a.cnt->sum_neigh, (unsigned long long) N);
+      atomicAdd(&a.cnt->sum_trip, (unsigned long long) N * (unsigned long long) (N > 0 ? N - 1 : 0) / 2ull);
+    }
+    if (N > C) {
+      if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
+      for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+      __syncwarp();
+      continue;
+    }
+    for (int t = lane; t < N * C / 2; t += 32) reinterpret_cast<unsigned *>(sSlot)[t] = 0xffffffffu;   // rows 0..N-1 of the slot table
+    __syncwarp();
+
+    // ---- 2. contributing pairs: folded triangle (rows it and N-2-it together hold N slots), ballot compaction
+    int Pv = 0;
+    for (int it = 0; 2 * it <= N - 2; it++) {
+      const int a1 = it, a2 = N - 2 - it, len1 = N - 1 - a1;
+      int pa = -1, pb = -1;
+      if (lane < len1) { pa = a1; pb = a1 + 1 + lane; }
+      else if (a2 != a1 && lane - len1 < it + 1) { pa = a2; pb = a2 + 1 + (lane - len1); }
+      bool ok = false;
+      if (pa >= 0) {
+        const BpGeom A = sN[pa], B = sN[pb];
+        if (A.r * CFLENGTH < Rc && B.r * CFLENGTH < Rc) {
+          const double ex = B.r * B.ux - A.r * A.ux, ey = B.r * B.uy - A.r * A.uy, ez = B.r * B.uz - A.r * A.uz;
+          ok = sqrt(ex * ex + ey * ey + ez * ez) * CFLENGTH < Rc;
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const int t = Pv + __popc(m & ((1u << lane) - 1u));
+        sPair[t] = (unsigned) pa | ((unsigned) pb << 16);
+        sSlot[pa * C + pb] = (unsigned short) t;
+        sSlot[pb * C + pa] = (unsigned short) t;
+      }
+      Pv += __popc(m);
+    }
+    __syncwarp();
+
+    // ---- 3. forward.  radial: one lane per neighbour; angular: one lane per contributing pair
+    for (int m = 0; m < npsf; m++) {
+      double acc = 0.0;
+      for (int s = lane; s < N; s += 32) {
+        const BpGeom g = sN[s];
+        const double rm = g.r * CFLENGTH;
+        if (rm < Rc_rad) {
+          double fc, dfc;
+          bp_fc(rm, Rc_rad, fc, dfc);
+          acc += exp(-P.rad_eta[m] * rm * rm) * fc;
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) sG[m] = (acc - P.sf_avg[m]) * P.sf_scale[m];
+    }
+    double G[NT];
+#pragma unroll
+    for (int n = 0; n < NT; n++) G[n] = 0.0;
+    for (int t = lane; t < Pv; t += 32) {
+      const unsigned pr = sPair[t];
+      const BpGeom A = sN[pr & 0xffffu], B = sN[pr >> 16];
+      double cosv, rjk, fcjk, dfcjk, E[NE], ex, ey, ez;
+      bp_pair_prims<NE>(A, B, Rc, rcinv, eta, cosv, rjk, fcjk, dfcjk, E, ex, ey, ez);
+      const double tfc = A.fc * B.fc * fcjk;
+      const double fm = 1.0 - cosv, fp = 1.0 + cosv;
+      double pm = fm > 0.0 ? fm : 0.0, pp = fp > 0.0 ? fp : 0.0;
+      int lg = 0;
+#pragma unroll
+      for (int z = 0; z < NZ; z++) {
+        while (lg < bp_zeta_log2<NZ>(z)) { pm *= pm; pp *= pp; lg++; }
+        const double coef = ldexp(1.0, 1 - (1 << bp_zeta_log2<NZ>(z)));
+#pragma unroll
+        for (int e = 0; e < NE; e++) {
+          const double w = coef * E[e] * tfc;
+          G[(e * NZ + z) * 2 + 0] = fma(w, pm, G[(e * NZ + z) * 2 + 0]);
+          G[(e * NZ + z) * 2 + 1] = fma(w, pp, G[(e * NZ + z) * 2 + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+      const double v = warp_sum(G[n]);
+      if (lane == 0) sG[npsf + n] = (v - P.sf_avg[npsf + n]) * P.sf_scale[npsf + n];
+    }
+    __syncwarp();
+
+    // ---- 4. MLP
+    const int elem = P.map[ti];
+    const double out = annp_mlp_warp(P, sW + elem * P.w_per_elem, sBias + elem * P.b_per_elem, sG, sdE, sH, sHd, sDel, lane);
+    const double e_i = out;
+    if (a.G_dbg) for (int n = lane; n < nsf; n += 32) { a.G_dbg[(size_t) ii * nsf + n] = sG[n]; a.dEdG_dbg[(size_t) ii * nsf + n] = sdE[n]; }
+    for (int n = lane; n < nsf; n += 32) sCn[n] = sdE[n] * P.sf_scale[n];
+    __syncwarp();
+    double c[NT];
+#pragma unroll
+    for (int n = 0; n < NT; n++) c[n] = sCn[npsf + n];
+
+    // ---- 5. backward.  radial part per neighbour, then pair chunks: gradients of both members -> slots -> ordered sums
+    double gx = 0, gy = 0, gz = 0;                      // d out / d x_s for s = lane (per Bohr)
+    if (lane < N) {
+      const BpGeom A = sN[lane];
+      const double ra_m = A.r * CFLENGTH;
+      if (ra_m < Rc_rad) {
+        double fc, dfc;
+        bp_fc(ra_m, Rc_rad, fc, dfc);
+        double acc = 0.0;
+        for (int m = 0; m < npsf; m++) {
+          const double et = P.rad_eta[m];
+          acc = fma(sCn[m], exp(-et * ra_m * ra_m) * (-fc * 2.0 * et * ra_m + dfc), acc);
+        }
+        gx = -acc * A.ux; gy = -acc * A.uy; gz = -acc * A.uz;
+      }
+    }
+    for (int c0 = 0; c0 < Pv; c0 += kBpPairCap) {
+      const int c1 = min(Pv, c0 + kBpPairCap);
+      for (int t = c0 + lane; t < c1; t += 32) {
+        const unsigned pr = sPair[t];
+        const BpGeom A = sN[pr & 0xffffu], B = sN[pr >> 16];      // A = the reference's j (first in the row), B = k
+        double cosv, rjk, fcjk, dfcjk, E[NE], ex, ey, ez;
+        bp_pair_prims<NE>(A, B, Rc, rcinv, eta, cosv, rjk, fcjk, dfcjk, E, ex, ey, ez);
+        const double tfc = A.fc * B.fc * fcjk;
+        const double fm = 1.0 - cosv, fp = 1.0 + cosv;
+        const bool okm = fm > 0.0, okp = fp > 0.0;
+        double pm = okm ? fm : 0.0, pp = okp ? fp : 0.0;
+        const double im = okm ? 1.0 / fm : 0.0, ip = okp ? 1.0 / fp : 0.0;
+        double S1 = 0.0, S2 = 0.0, S3 = 0.0;
+        int lg = 0;
+#pragma unroll
+        for (int z = 0; z < NZ; z++) {
+          while (lg < bp_zeta_log2<NZ>(z)) { pm *= pm; pp *= pp; lg++; }
+          const double zeta = (double) (1 << bp_zeta_log2<NZ>(z));
+          const double coef = ldexp(1.0, 1 - (1 << bp_zeta_log2<NZ>(z)));
+          double tm = 0.0, tp = 0.0, um = 0.0, up = 0.0;
+#pragma unroll
+          for (int e = 0; e < NE; e++) {
+            const double cm = c[(e * NZ + z) * 2 + 0] * E[e], cp = c[(e * NZ + z) * 2 + 1] * E[e];
+            tm += cm; tp += cp;
+            um = fma(eta[e], cm, um); up = fma(eta[e], cp, up);
+          }
+          const double Tm = coef * pm, Tp = coef * pp;
+          S3 = fma(Tm, tm, fma(Tp, tp, S3));
+          S2 = fma(Tm, um, fma(Tp, up, S2));
+          S1 = fma(zeta * Tp * ip, tp, fma(-zeta * Tm * im, tm, S1));
+        }
+        const double k1 = S1 * tfc / CFLENGTH, k2 = S2 * tfc;
+        const double rjkinv = 1.0 / rjk;
+        const double djx = ex * rjkinv, djy = ey * rjkinv, djz = ez * rjkinv;       // dr_djk = (x_j - x_k)/r_jk
+        const double rik_m = B.r * CFLENGTH, rij_m = A.r * CFLENGTH;
+        double *T = sT + (size_t) (t - c0) * 6;
+        {   // first member j = A
+          const double rinv = 1.0 / A.r;
+          const double cx = (cosv * A.ux - B.ux) * rinv, cy = (cosv * A.uy - B.uy) * rinv, cz = (cosv * A.uz - B.uz) * rinv;
+          const double q1 = B.fc * A.dfc * fcjk, q2 = B.fc * A.fc * dfcjk;
+          T[0] = k1 * cx - k2 * 2.0 * (rij_m * (-A.ux) + rik_m * djx) + S3 * (q1 * (-A.ux) + q2 * djx);
+          T[1] = k1 * cy - k2 * 2.0 * (rij_m * (-A.uy) + rik_m * djy) + S3 * (q1 * (-A.uy) + q2 * djy);
+          T[2] = k1 * cz - k2 * 2.0 * (rij_m * (-A.uz) + rik_m * djz) + S3 * (q1 * (-A.uz) + q2 * djz);
+        }
+        {   // second member k = B: r_ik in both parts of term2, as the reference (:734-735)
+          const double rinv = 1.0 / B.r;
+          const double cx = (cosv * B.ux - A.ux) * rinv, cy = (cosv * B.uy - A.uy) * rinv, cz = (cosv * B.uz - A.uz) * rinv;
+          const double q1 = A.fc * B.dfc * fcjk, q2 = -A.fc * B.fc * dfcjk;
+          T[3] = k1 * cx - k2 * 2.0 * (rik_m * (-B.ux) - rik_m * djx) + S3 * (q1 * (-B.ux) + q2 * djx);
+          T[4] = k1 * cy - k2 * 2.0 * (rik_m * (-B.uy) - rik_m * djy) + S3 * (q1 * (-B.uy) + q2 * djy);
+          T[5] = k1 * cz - k2 * 2.0 * (rik_m * (-B.uz) - rik_m * djz) + S3 * (q1 * (-B.uz) + q2 * djz);
+        }
+      }
+      __syncwarp();
+      if (lane < N) {                                   // ordered sum over partners b = 0..N-1 of this chunk's slots
+        const unsigned short *row = sSlot + lane * C;
+        for (int b = 0; b < N; b++) {
+          const int t = row[b];
+          if (t >= c0 && t < c1) {
+            const double *T = sT + (size_t) (t - c0) * 6 + (lane < b ? 0 : 3);
+            gx += T[0]; gy += T[1]; gz += T[2];
+          }
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- 6. output
+    double fix = 0, fiy = 0, fiz = 0;
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0, v5 = 0;
+    if (lane < N) {
+      const BpGeom A = sN[lane];
+      const double Fx = -gx, Fy = -gy, Fz = -gz;        // Fj of the reference before CFFORCE (:180-190)
+      const int q = spos[lane];
+      a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
+      fix = -Fx * CFFORCE; fiy = -Fy * CFFORCE; fiz = -Fz * CFFORCE;
+      if (a.vir_c || a.vpair) {
+        const double X = A.r * A.ux, Y = A.r * A.uy, Z = A.r * A.uz;
+        v0 = -X * Fx; v1 = -Y * Fy; v2 = -Z * Fz; v3 = -X * Fy; v4 = -X * Fz; v5 = -Y * Fz;
+        if (a.vpair) {
+          double *vp = a.vpair + (size_t) (p0 + q) * 6;
+          vp[0] = v0; vp[1] = v1; vp[2] = v2; vp[3] = v3; vp[4] = v4; vp[5] = v5;
+        }
+      }
+    }
+    fix = warp_sum(fix); fiy = warp_sum(fiy); fiz = warp_sum(fiz);
+    if (lane == 0) a.fself[ii] = make_double4(fix, fiy, fiz, e_i);
+    if (a.vir_c) {
+      v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
+      v3 = warp_sum(v3); v4 = warp_sum(v4); v5 = warp_sum(v5);
+      if (lane == 0) {
+        double *vc = a.vir_c + (size_t) ii * 6;
+        vc[0] = v0; vc[1] = v1; vc[2] = v2; vc[3] = v3; vc[4] = v4; vc[5] = v5;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 }    // namespace
 
 // 1 when the angular table has the product structure the fast kernel is instantiated for, else 0 (generic kernel)
@@ -612,9 +930,21 @@ size_t annp_bp_smem_bytes(const DevParams &hp, int capacity) {
   return blk + kWarps * per_warp;
 }
 
+static size_t annp_bp_pair_smem_bytes(const DevParams &hp) {
+  const int C = 32;
+  size_t blk = (size_t) (hp.nelements * (hp.w_per_elem + hp.b_per_elem)) * sizeof(double);
+  blk = (blk + 15) & ~(size_t) 15;
+  size_t per_warp = ((size_t) 6 * C + (size_t) 6 * kBpPairCap + 3 * hp.nsf + (size_t) 2 * hp.nlayers * hp.nnod + 2 * hp.nnod) * sizeof(double) +
+                    (size_t) (C * (C - 1) / 2) * sizeof(unsigned) + (size_t) C * C * sizeof(unsigned short) + (size_t) C * sizeof(int);
+  per_warp = (per_warp + 15) & ~(size_t) 15;
+  return blk + kWarps * per_warp;
+}
+
 cudaError_t annp_bp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream) {
-  const size_t smem = annp_bp_smem_bytes(hp, args.capacity);
-  void (*kern)(const ForceArgs) = hp.bp_layout == 1 ? annp_bp_fast_kernel<3, 4> : annp_bp_force_kernel;
+  // product-structured table: pair-compaction kernel while the tile fits one warp, lane-per-neighbour kernel beyond
+  const bool pairk = hp.bp_layout == 1 && args.capacity <= 32;
+  const size_t smem = pairk ? annp_bp_pair_smem_bytes(hp) : annp_bp_smem_bytes(hp, args.capacity);
+  void (*kern)(const ForceArgs) = pairk ? annp_bp_pair_kernel<3, 4> : (hp.bp_layout >= 1 ? annp_bp_fast_kernel<3, 4> : annp_bp_force_kernel);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   if (e != cudaSuccess) return e;
   int per_sm = 0;

@@ -18,9 +18,11 @@ from meng_zhang_b200.pair_anna import PairANNAADPGPU, read_anna_potential
 pytestmark = pytest.mark.gpu
 
 
-def make_ni(pot_file, elems=("Ni",), generic=False):
-    # variant decided from the file (coefficient blocks -> Ni copy); generic=True forces the table-driven kernel
-    pair = PairANNPGPU(ntypes=len(elems), variant=(capi.VARIANT_NI | capi.VARIANT_FLAG_GENERIC) if generic else None)
+def make_ni(pot_file, elems=("Ni",), kernel="pair"):
+    # variant decided from the file (coefficient blocks -> Ni copy); the flags force one of the three kernels:
+    # "pair" (default for tiles <= 32: pair compaction), "lane" (lane per neighbour), "generic" (table driven, pow/exp)
+    flag = {"pair": None, "lane": capi.VARIANT_NI | capi.VARIANT_FLAG_NOPAIR, "generic": capi.VARIANT_NI | capi.VARIANT_FLAG_GENERIC}[kernel]
+    pair = PairANNPGPU(ntypes=len(elems), variant=flag)
     pair.settings([])
     pair.coeff(["*", "*", pot_file] + list(elems))
     pair.init_style()
@@ -35,11 +37,11 @@ def make_anna(pot_file, elems=("Fe",)):
     return pair
 
 
-@pytest.mark.parametrize("generic", [False, True], ids=["fast", "generic"])
+@pytest.mark.parametrize("kernel", ["pair", "lane", "generic"])
 @pytest.mark.parametrize("name", util.NI_CASES)
-def test_ni_golden_case(name, generic, ni_pot_file):
+def test_ni_golden_case(name, kernel, ni_pot_file):
     cfg, elems, ref = util.load_case(name, "annp_ni")
-    pair = make_ni(ni_pot_file, elems, generic)
+    pair = make_ni(ni_pot_file, elems, kernel)
     f = pair.compute(3, 1 + 4, cfg, ago=0)
     assert np.abs(pair.eatom - ref["eatom"]).max() <= 1e-10
     assert abs(pair.eng_vdwl - ref["eng_vdwl"]) <= 1e-9
