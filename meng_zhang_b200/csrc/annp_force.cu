@@ -212,15 +212,16 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
   const int nsf = NPSF + NTSF, nnod = P.nnod, nl = P.nlayers, nt1 = P.ntypes + 1;
   const int wtot = P.nelements * P.w_per_elem, btot = P.nelements * P.b_per_elem;
 
-  // ---- block-shared parameters
-  double *sW = reinterpret_cast<double *>(smem_raw);
-  double *sBias = sW + wtot;
-  double *sScale = sBias + btot;
+  // ---- block-shared parameters.  The network weights stay in global memory (3.7 KB, L1 resident, touched by <= 28
+  // lanes for ~1 % of an atom's time): keeping them out of shared memory lets a FOURTH block fit on the SM
+  // (59.9 -> 56.2 KB per block at a 128-slot tile), i.e. 4 instead of 3 warps per scheduler to hide FP64 latency.
+  double *sScale = reinterpret_cast<double *>(smem_raw);
   double *sAvg = sScale + nsf;
   double *blk_end = sAvg + nsf;
+  const double *__restrict__ sW = P.weights;
+  const double *__restrict__ sBias = P.bias;
   const double *__restrict__ gC2M = P.cheb2mono;     // [NTSF][NTSF] Chebyshev -> monomial(z) matrix (L1/L2 resident)
-  for (int t = threadIdx.x; t < wtot; t += blockDim.x) sW[t] = P.weights[t];
-  for (int t = threadIdx.x; t < btot; t += blockDim.x) sBias[t] = P.bias[t];
+  (void) wtot; (void) btot;
   for (int t = threadIdx.x; t < nsf; t += blockDim.x) { sScale[t] = P.sf_scale[t]; sAvg[t] = P.sf_avg[t]; }
 
   // ---- per-warp region
@@ -577,7 +578,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
 
 size_t annp_force_smem_bytes(const DevParams &hp, int capacity) {
   const int nsf = hp.nsf, nl = hp.nlayers, nnod = hp.nnod;
-  size_t blk = (size_t) (hp.nelements * (hp.w_per_elem + hp.b_per_elem) + 2 * nsf) * sizeof(double);
+  size_t blk = (size_t) (2 * nsf) * sizeof(double);
   blk = (blk + 15) & ~(size_t) 15;
   size_t per_warp = ((size_t) 11 * capacity + 2 * hp.ntsf + 2 * hp.npsf + 2 * nsf + (size_t) 2 * nl * nnod + 2 * nnod) * sizeof(double) +
                     (size_t) capacity * sizeof(int);

@@ -1,0 +1,134 @@
+"""The other BASELINE configurations, end to end on the device (bench.py measures the headline one, configs[4]):
+
+    config 2   fcc Ni ANNP (Ni copy of the style), 32 000 atoms, NVT 300 K
+    config 3   bcc Fe ANNP, 40x40x80 cells = 256 000 atoms, NPT 300 K (the deck's `y 0 0 1` coupling)
+    config 4   bcc Fe screw dislocation (structures.screw_dislocation((22, 38, 50)) ~ 5.1e5 atoms), free x / y surfaces,
+               periodic z, rim atoms (type 2) held fixed, NVE, decomposed over the ranks it is launched on
+    anna       bcc Fe ANNA-ADP, 40^3 cells = 128 000 atoms, NVT 300 K
+
+    python scripts/bench_configs.py [--steps 100] [--only 2,3,4,anna]
+    python -m torch.distributed.run --nproc-per-node 8 ... scripts/bench_configs.py --only 4
+
+One JSON line per configuration on rank 0: atom-steps/s (CUDA events, max over ranks), ms per step, temperature /
+pressure at the end as a sanity value.  Development aid + evidence for profiles/, not the driver's bench.
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import util  # noqa: E402
+from meng_zhang_b200 import lattice as L, structures as S  # noqa: E402
+from meng_zhang_b200.md import DomainMD, decompose, rank_coords  # noqa: E402
+from meng_zhang_b200.pair import PairANNPGPU  # noqa: E402
+from meng_zhang_b200.pair_anna import PairANNAADPGPU  # noqa: E402
+
+
+def make_pair(kind, dev):
+    tmp = tempfile.gettempdir()
+    if kind == "ni":
+        pot, elem, cls = util.write_ni_potential(os.path.join(tmp, f"bc_ni_{dev}.ann")), "Ni", PairANNPGPU
+    elif kind == "anna":
+        pot, elem, cls = util.write_anna_fe_potential(os.path.join(tmp, f"bc_anna_{dev}.anna")), "Fe", PairANNAADPGPU
+    else:
+        pot, elem, cls = util.write_fe_potential(os.path.join(tmp, f"bc_fe_{dev}.ann")), "Fe", PairANNPGPU
+    pair = cls(ntypes=2 if kind == "fe2" else 1, device=dev)
+    pair.settings([])
+    pair.coeff(["*", "*", pot] + [elem] * pair.ntypes)
+    pair.init_style()
+    return pair
+
+
+def run_case(name, kind, x_all, box, mass, periodic, ensemble, steps, rank, world, local, dev, types=None, frozen=None):
+    grid = decompose(world)
+    coords = rank_coords(rank, grid)
+    lo = np.array([box[d] * coords[d] / grid[d] for d in range(3)])
+    hi = np.array([box[d] * (coords[d] + 1) / grid[d] for d in range(3)])
+    x_all = L.wrap(x_all, box, periodic)
+    inside = np.ones(len(x_all), dtype=bool)
+    for d in range(3):      # free surfaces: the outermost bricks own whatever lies beyond the nominal box face
+        lo_d = -np.inf if (coords[d] == 0 and not periodic[d]) else lo[d]
+        hi_d = np.inf if (coords[d] == grid[d] - 1 and not periodic[d]) else hi[d]
+        inside &= (x_all[:, d] >= lo_d) & (x_all[:, d] < hi_d)
+    pair = make_pair(kind, local)
+    md = DomainMD(pair, x_all[inside], box, grid=grid, rank=rank, device=dev, mass=mass, dt=0.001, periodic=periodic,
+                  type_local=None if types is None else types[inside], frozen_local=None if frozen is None else frozen[inside])
+    md.set_velocities(300.0, 4928459)
+    md.reneighbor()
+    if ensemble == "nve":
+        md.compute(eflag=True)
+        stepper = md.step
+    else:
+        p_flag = (0, 1, 0) if ensemble == "npt" else (0, 0, 0)
+        md.fix_nh(300.0, 300.0, 0.1, p_flag=p_flag, p_start=(0.0,) * 3, p_stop=(0.0,) * 3, p_damp=(1.0,) * 3)
+        stepper = md.step_nh
+    for _ in range(5):
+        stepper()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        stepper()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t) / steps
+    st = pair.stats()
+    extra = {}
+    if ensemble != "nve":
+        s = md.nh_state()
+        extra = {"T": s.t_current, "p_bar": list(s.p_current[:]), "box": [s.boxhi[d] - s.boxlo[d] for d in range(3)]}
+    nat = torch.tensor([float(md.nlocal)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(nat)
+    if rank == 0:
+        print(json.dumps({"config": name, "atoms": int(nat), "n_gpus": world, "grid": "x".join(map(str, grid)), "ensemble": ensemble,
+                          "steps": steps, "ms_per_step": ms, "atom_steps_per_s": float(nat) / (ms * 1e-3),
+                          "ns_per_day": 86400.0 / (ms * 1e-3) * 1e-6, "neighbors_in_cutoff": st.avg_neigh_cut,
+                          "list_neighbors_max": st.max_neigh_list, **extra}), flush=True)
+    pair.clear()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--only", default="2,3,4,anna")
+    a = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    only = a.only.split(",")
+    pbc = (True, True, True)
+    if "2" in only:
+        x, box = L.fcc(20, 20, 20)
+        run_case("2: fcc Ni ANNP 32 000 atoms NVT 300 K", "ni", L.perturb(x, 0.02, 1), box, 58.6934, pbc, "nvt", a.steps, rank, world, local, dev)
+    if "3" in only:
+        x, box = L.bcc(40, 40, 80)
+        run_case("3: bcc Fe ANNP 256 000 atoms NPT 300 K (y 0 0 1)", "fe", L.perturb(x, 0.02, 2), box, 55.845, pbc, "npt", a.steps, rank, world, local, dev)
+    if "4" in only:
+        xs, box, types, core = S.screw_dislocation((22, 38, 50))
+        run_case("4: bcc Fe screw dislocation, free x/y, periodic z, fixed rim, NVE", "fe", xs, box, 55.845, (False, False, True), "nve",
+                 a.steps, rank, world, local, dev, frozen=(types == 2))
+    if "anna" in only:
+        x, box = L.bcc(40, 40, 40)
+        run_case("anna: bcc Fe ANNA-ADP 128 000 atoms NVT 300 K", "anna", L.perturb(x, 0.02, 3), box, 55.845, pbc, "nvt", a.steps, rank, world, local, dev)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
