@@ -241,7 +241,12 @@ def run_ours(args):
                        "neighbors_in_cutoff": st.avg_neigh_cut, "list_neighbors": st0.max_neigh_list,
                        "l2_policy": "inputs larger than L2 (neighbour list + pair-force buffers are GBs per step)"},
             "roofline": {"bound": "fp64", "kernel": "annp_force_kernel<9,19>", "achieved": achieved_tf, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at exactly this workload
+                         # (profiles/r1b_force_kernel.md: 0.535 GB read + 3.737 GB written, 32 B per list entry of
+                         # pair forces); algorithmic bytes are ~0.94 kB/atom = 0.49 GB, the rest is the deterministic
+                         # scatter buffer, 1.8 % of the measured HBM peak and hidden behind the FP64 pipe
+                         "traffic": 4.2727e9 if (cells == 64 and world == 1) else None,
                          "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / (ms_total / args.steps),
                          "flop_per_atom_step": flop_per_launch / nlocal,
                          "peak_source": "measured on this GPU by annp_b200_fp64_peak_tflops (pure DFMA loop); "

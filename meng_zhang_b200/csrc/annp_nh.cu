@@ -453,6 +453,7 @@ static int nh_partial(annp_b200_nh h, int nlocal) {
 
 int annp_b200_nh_reduce(annp_b200_nh h, int nlocal, const double *d_v, const double *d_engvir, double *d_red12, void *stream) {
   if (!h || nlocal < 0 || !d_v || !d_red12) return ANNP_B200_EINVAL;
+  if (cudaSetDevice(h->device) != cudaSuccess) return ANNP_B200_ECUDA;
   if (nh_partial(h, nlocal)) return ANNP_B200_ENOMEM;
   cudaStream_t s = (cudaStream_t) stream;
   const int nb = (nlocal + kRedSlice - 1) / kRedSlice;
@@ -463,6 +464,7 @@ int annp_b200_nh_reduce(annp_b200_nh h, int nlocal, const double *d_v, const dou
 
 int annp_b200_nh_setup(annp_b200_nh h, const double *d_red12, void *stream) {
   if (!h || !d_red12) return ANNP_B200_EINVAL;
+  if (cudaSetDevice(h->device) != cudaSuccess) return ANNP_B200_ECUDA;
   k_nh_setup<<<1, 1, 0, (cudaStream_t) stream>>>(h->d_state, d_red12);
   return cudaGetLastError() == cudaSuccess ? ANNP_B200_OK : ANNP_B200_ECUDA;
 }
@@ -470,6 +472,7 @@ int annp_b200_nh_setup(annp_b200_nh h, const double *d_red12, void *stream) {
 int annp_b200_nh_initial(annp_b200_nh h, int nlocal, double *d_x, double *d_v, const double *d_f, int nsend, double *d_send_shift,
                          void *stream) {
   if (!h || nlocal < 0 || !d_x || !d_v || !d_f) return ANNP_B200_EINVAL;
+  if (cudaSetDevice(h->device) != cudaSuccess) return ANNP_B200_ECUDA;
   cudaStream_t s = (cudaStream_t) stream;
   k_nh_begin<<<1, 1, 0, s>>>(h->d_state);
   if (nlocal > 0) k_nh_initial<<<grid_for(3LL * nlocal, 256), 256, 0, s>>>(h->d_state, nlocal, d_x, d_v, d_f);
@@ -480,6 +483,7 @@ int annp_b200_nh_initial(annp_b200_nh h, int nlocal, double *d_x, double *d_v, c
 int annp_b200_nh_final_kick(annp_b200_nh h, int nlocal, double *d_v, const double *d_f, const double *d_engvir, double *d_red12,
                             void *stream) {
   if (!h || nlocal < 0 || !d_v || !d_f || !d_red12) return ANNP_B200_EINVAL;
+  if (cudaSetDevice(h->device) != cudaSuccess) return ANNP_B200_ECUDA;
   if (nh_partial(h, nlocal)) return ANNP_B200_ENOMEM;
   cudaStream_t s = (cudaStream_t) stream;
   const int nb = (nlocal + kRedSlice - 1) / kRedSlice;
@@ -490,6 +494,7 @@ int annp_b200_nh_final_kick(annp_b200_nh h, int nlocal, double *d_v, const doubl
 
 int annp_b200_nh_final_scale(annp_b200_nh h, int nlocal, double *d_v, const double *d_red12, void *stream) {
   if (!h || nlocal < 0 || !d_v || !d_red12) return ANNP_B200_EINVAL;
+  if (cudaSetDevice(h->device) != cudaSuccess) return ANNP_B200_ECUDA;
   cudaStream_t s = (cudaStream_t) stream;
   k_nh_end<<<1, 1, 0, s>>>(h->d_state, d_red12);
   if (nlocal > 0 && h->host.tstat) k_nh_scale_v<<<grid_for(3LL * nlocal, 256), 256, 0, s>>>(h->d_state, nlocal, d_v);
@@ -498,6 +503,7 @@ int annp_b200_nh_final_scale(annp_b200_nh h, int nlocal, double *d_v, const doub
 
 int annp_b200_nh_get_state(annp_b200_nh h, annp_b200_nh_state *out, void *stream) {
   if (!h || !out) return ANNP_B200_EINVAL;
+  if (cudaSetDevice(h->device) != cudaSuccess) return ANNP_B200_ECUDA;
   cudaStream_t s = (cudaStream_t) stream;
   if (cudaMemcpyAsync(&h->host, h->d_state, sizeof(NhState), cudaMemcpyDeviceToHost, s) != cudaSuccess) return ANNP_B200_ECUDA;
   if (cudaStreamSynchronize(s) != cudaSuccess) return ANNP_B200_ECUDA;
