@@ -99,7 +99,7 @@ class DomainMD:
     """One rank's sub-domain, device resident.  `pair` is an initialised PairANNPGPU."""
 
     def __init__(self, pair, x_local, box, grid=(1, 1, 1), rank=0, device=None, type_local=None,
-                 skin=2.0, mass=55.845, dt=0.001, group=None, periodic=(True, True, True), frozen_local=None):
+                 skin=2.0, mass=55.845, dt=0.001, group=None, periodic=(True, True, True), frozen_local=None, gid_local=None):
         """periodic: per-axis `boundary p` (True) or free surface (False).  frozen_local: boolean mask of atoms held
         fixed (force and velocity zeroed every step: `fix setforce 0 0 0` on the rim of the dislocation cylinder)."""
         self.periodic = tuple(bool(p) for p in periodic)
@@ -126,6 +126,10 @@ class DomainMD:
         self.ke = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self.x = self.f = self.type = None
         self.nsteps = 0
+        self.box_origin = np.zeros(3)
+        # global atom ids (travel with the atoms when they migrate); default: rank-concatenated numbering
+        self.gid = None if gid_local is None else torch.as_tensor(np.ascontiguousarray(gid_local), dtype=torch.int64, device=self.dev)
+        self.migrated = 0
         self.frozen_idx = None
         if frozen_local is not None and np.any(frozen_local):
             self.frozen_idx = torch.as_tensor(np.nonzero(np.asarray(frozen_local))[0], dtype=torch.int64, device=self.dev)
@@ -150,9 +154,56 @@ class DomainMD:
             self.v.index_fill_(0, self.frozen_idx, 0.0)
 
     # ------------------------------------------------------------------ re-neighbouring (ago == 0)
+    def _migrate(self, xl, fl):
+        """Atom migration of LAMMPS' re-neighbouring (Comm::exchange): wrap positions into the periodic box and hand
+        every atom to the rank whose brick now contains it, together with its velocity, last force (the next half kick
+        needs it), type, frozen flag and global id.  One all_to_all of the per-destination counts and one of the payload;
+        arrival order is (source rank, source order), so the result is deterministic."""
+        origin = torch.as_tensor(self.box_origin, dtype=torch.float64, device=self.dev)
+        boxd = torch.as_tensor(self.box, dtype=torch.float64, device=self.dev)
+        per = torch.as_tensor(self.periodic, dtype=torch.bool, device=self.dev)
+        xl = torch.where(per, xl - torch.floor((xl - origin) / boxd) * boxd, xl)
+        if self.gid is None:
+            counts = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+            counts[self.rank] = self.nlocal
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(counts, group=self.group)
+            start = int(counts[: self.rank].sum())
+            self.gid = torch.arange(start, start + self.nlocal, dtype=torch.int64, device=self.dev)
+        if self.world == 1:
+            return xl, fl
+        import torch.distributed as dist
+        grid = torch.as_tensor(self.grid, dtype=torch.float64, device=self.dev)
+        cell = torch.floor((xl - origin) / (boxd / grid)).clamp_(min=0).to(torch.int64)
+        cell = torch.minimum(cell, torch.as_tensor(self.grid, dtype=torch.int64, device=self.dev) - 1)
+        dest = cell[:, 0] + cell[:, 1] * self.grid[0] + cell[:, 2] * self.grid[0] * self.grid[1]
+        order = torch.argsort(dest, stable=True)
+        send_counts = torch.bincount(dest, minlength=self.world)
+        frozen = torch.zeros(self.nlocal, dtype=torch.float64, device=self.dev)
+        if self.frozen_idx is not None:
+            frozen[self.frozen_idx] = 1.0
+        payload = torch.cat([xl, self.v, fl, self._type_local.to(torch.float64)[:, None], frozen[:, None],
+                             self.gid.to(torch.float64)[:, None]], dim=1)[order].contiguous()
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = [int(c) for c in send_counts.cpu()], [int(c) for c in recv_counts.cpu()]
+        self.migrated = self.nlocal - sc[self.rank]
+        got = torch.empty((sum(rc), payload.shape[1]), dtype=torch.float64, device=self.dev)
+        dist.all_to_all_single(got, payload, rc, sc, group=self.group)
+        self.nlocal = got.shape[0]
+        self.v = got[:, 3:6].contiguous()
+        self._type_local = got[:, 9].to(torch.int32).contiguous()
+        fz = torch.nonzero(got[:, 10] > 0.5).flatten()
+        self.frozen_idx = fz if fz.numel() else None
+        self.gid = got[:, 11].to(torch.int64).contiguous()
+        return got[:, 0:3].contiguous(), got[:, 6:9].contiguous()
+
     def reneighbor(self):
-        """Rebuild send lists, ghosts and the device neighbour list from the current local positions."""
+        """Migrate atoms, rebuild send lists, ghosts and the device neighbour list from the current local positions."""
         xl = (self.x[: self.nlocal] if self.x is not None else self._x_local0)
+        fl = self.f[: self.nlocal] if self.f is not None else torch.zeros_like(xl)
+        xl, fl = self._migrate(xl, fl)
         xl_host = xl.cpu().numpy()
         cutghost = self.cut + self.skin
         idx, shift, send_counts = build_send_lists(xl_host, self.lo, self.hi, self.box, self.grid, self.coords, cutghost, self.periodic)
@@ -174,6 +225,7 @@ class DomainMD:
         x[: self.nlocal] = xl
         self.x = x
         self.f = torch.zeros((nall, 3), dtype=torch.float64, device=self.dev)
+        self.f[: self.nlocal] = fl           # forces of the last evaluation: the next half kick uses them
         if self.world > 1:
             self.sendbuf = torch.empty((self.nsend, 3), dtype=torch.float64, device=self.dev)
             self.recvbuf = torch.empty((self.nsend, 3), dtype=torch.float64, device=self.dev)
@@ -190,9 +242,9 @@ class DomainMD:
             tghost = tl[self.send_index.long()]
         self.type = torch.cat([tl, tghost]).contiguous()
         self.forward_comm()
-        lo = (self.lo - cutghost - 1e-6).astype(np.float64)
-        hi = (self.hi + cutghost + 1e-6).astype(np.float64)
-        # locals may have drifted slightly outside the brick between re-neighbourings
+        # bounding box of everything the list sees (free surfaces may lie anywhere outside the nominal brick)
+        lo = (self.x.amin(dim=0).cpu().numpy() - 1e-6).astype(np.float64) if nall else (self.lo - cutghost)
+        hi = (self.x.amax(dim=0).cpu().numpy() + 1e-6).astype(np.float64) if nall else (self.hi + cutghost)
         self._ck(self.L.annp_b200_neigh_build(self.h, self.nlocal, nall, C.c_void_p(self.x.data_ptr()),
                                               lo.ctypes.data_as(capi.c_double_p), hi.ctypes.data_as(capi.c_double_p),
                                               float(cutghost), self._stream()))

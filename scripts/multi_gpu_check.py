@@ -42,6 +42,59 @@ def make_pair(dev, kind="fe"):
     return pair
 
 
+def migration_check(rank, world, local, dev, grid):
+    """(f) atoms drifting through the sub-domain boundaries: decomposed NVE run with migration at every re-neighbouring
+    vs the same run on one GPU, compared atom by atom through the global ids."""
+    coords = rank_coords(rank, grid)
+    cells = (8 * grid[0], 8 * grid[1], 8 * grid[2])
+    x_all, box = L.bcc(*cells)
+    x_all = L.wrap(L.perturb(x_all, 0.05, 5), box)
+    rng = np.random.default_rng(9)
+    v_all = rng.normal(size=x_all.shape) * 2.0
+    v_all -= v_all.mean(axis=0)
+    v_all += np.array([30.0, 17.0, -11.0])             # A/ps: 12 A of drift in 400 steps, far beyond one brick's skin
+    lo = np.array([box[d] * coords[d] / grid[d] for d in range(3)])
+    hi = np.array([box[d] * (coords[d] + 1) / grid[d] for d in range(3)])
+    mine = np.all((x_all >= lo) & (x_all < hi), axis=1)
+    pair = make_pair(local, "fe")
+    md = DomainMD(pair, x_all[mine], box, grid=grid, rank=rank, device=dev, gid_local=np.nonzero(mine)[0])
+    md.v = torch.as_tensor(v_all[mine], device=dev)
+    md.reneighbor()
+    md.compute(eflag=True)
+    out = md.run(400, check_every=5, thermo_every=100)
+    moved = torch.tensor([float(md.migrated)], dtype=torch.float64, device=dev)
+    n_all = len(x_all)
+    xg = torch.zeros((n_all, 3), dtype=torch.float64, device=dev)
+    cnt = torch.zeros(n_all, dtype=torch.float64, device=dev)
+    xg[md.gid] = md.x[: md.nlocal]
+    cnt[md.gid] = 1.0
+    dist.all_reduce(xg)
+    dist.all_reduce(cnt)
+    nl = torch.tensor([float(md.nlocal)], dtype=torch.float64, device=dev)
+    dist.all_reduce(nl)
+    ok = True
+    if rank == 0:
+        pair1 = make_pair(local, "fe")
+        md1 = DomainMD(pair1, x_all, box, grid=(1, 1, 1), rank=0, device=dev)
+        md1.v = torch.as_tensor(v_all, device=dev)
+        md1.reneighbor()
+        md1.compute(eflag=True)
+        out1 = md1.run(400, check_every=5, thermo_every=100)
+        boxd = torch.as_tensor(box, device=dev)
+        d = xg - md1.x[: md1.nlocal][torch.argsort(md1.gid)]
+        d -= torch.round(d / boxd) * boxd
+        dx = float(d.abs().max())
+        de = max(abs((a[1] + a[2]) - (b[1] + b[2])) for a, b in zip(out, out1))
+        drift = abs((out[-1][1] + out[-1][2]) - (out[0][1] + out[0][2])) / n_all
+        ok = dx < 1e-9 and de < 1e-7 and int(nl) == n_all and float(cnt.min()) == 1.0 and md.rebuilds == md1.rebuilds and md.rebuilds > 5
+        print(f"multi_gpu_check[migration] world={world} atoms={n_all}: {md.rebuilds} rebuilds, every atom owned exactly once: {float(cnt.min()) == 1.0 and int(nl) == n_all}, "
+              f"max|dx| vs one GPU after 400 steps {dx:.3e}, |dE_tot| {de:.3e} eV, NVE drift {drift:.2e} eV/atom  {'ok' if ok else 'FAIL'}")
+        pair1.clear()
+    pair.clear()
+    dist.barrier()
+    return ok
+
+
 def variant_checks(rank, world, local, dev, grid):
     """(d) npt and (e) the other two potentials, decomposed vs one domain."""
     ok = True
@@ -161,8 +214,9 @@ def main():
         ok = df < 1e-11 and dx < 1e-11 and de < 1e-13
     pair.clear()
     okv = variant_checks(rank, world, local, dev, grid)
+    okm = migration_check(rank, world, local, dev, grid)
     if rank == 0:
-        ok = ok and okv
+        ok = ok and okv and okm
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
     dist.barrier()
     dist.destroy_process_group()

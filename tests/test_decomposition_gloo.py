@@ -117,3 +117,57 @@ def test_decomposed_forces_equal_single_domain(world, cells, tmp_path, fe_pot_fi
         assert abs(float(z["e"][0]) - ref["eng_vdwl"]) < 1e-9 * abs(ref["eng_vdwl"])
     assert np.all(seen == 1)
     assert np.abs(got - fref).max() < 1e-11
+
+
+# ------------------------------------------------------------------------------------------------ atom migration
+def _migrate_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from meng_zhang_b200.md import DomainMD
+        grid = decompose(world)
+        box = np.array([20.0, 16.0, 12.0])
+        rng = np.random.default_rng(100)
+        n_all = 4000
+        x_all = rng.uniform(0.0, 1.0, size=(n_all, 3)) * box
+        coords = rank_coords(rank, grid)
+        lo = np.array([box[d] * coords[d] / grid[d] for d in range(3)])
+        hi = np.array([box[d] * (coords[d] + 1) / grid[d] for d in range(3)])
+        mine = np.all((x_all >= lo) & (x_all < hi), axis=1)
+        gid = np.nonzero(mine)[0]
+        # every atom moves by up to +-6 A (some leave through periodic faces, some cross to non-adjacent bricks)
+        disp = np.random.default_rng(7).uniform(-6.0, 6.0, size=(n_all, 3))
+        md = DomainMD.__new__(DomainMD)                       # bookkeeping only: no GPU, no pair style
+        md.dev, md.world, md.rank, md.group, md.grid = torch.device("cpu"), world, rank, None, grid
+        md.box, md.box_origin, md.periodic = box, np.zeros(3), (True, True, True)
+        md.nlocal = int(mine.sum())
+        md.v = torch.from_numpy(np.stack([gid, 2.0 * gid, 3.0 * gid], axis=1).astype(np.float64))     # recognisable payload
+        md._type_local = torch.from_numpy((1 + gid % 2).astype(np.int32))
+        fz = np.nonzero(gid % 5 == 0)[0]
+        md.frozen_idx = torch.from_numpy(fz.astype(np.int64))
+        md.gid = torch.from_numpy(gid.astype(np.int64))
+        xl = torch.from_numpy(x_all[mine] + disp[mine])
+        fl = torch.from_numpy(np.stack([-1.0 * gid, 0.5 * gid, 7.0 + gid], axis=1).astype(np.float64))
+        xn, fn = md._migrate(xl, fl)
+        g = md.gid.numpy()
+        assert np.all((xn.numpy() >= lo - 1e-12) & (xn.numpy() < hi + 1e-12)), "an atom is outside its new owner's brick"
+        want = x_all[g] + disp[g]
+        want -= np.floor(want / box) * box
+        assert np.abs(xn.numpy() - want).max() < 1e-12
+        assert np.array_equal(md.v.numpy(), np.stack([g, 2.0 * g, 3.0 * g], axis=1))
+        assert np.array_equal(fn.numpy(), np.stack([-1.0 * g, 0.5 * g, 7.0 + g], axis=1))
+        assert np.array_equal(md._type_local.numpy(), 1 + g % 2)
+        frozen = np.zeros(md.nlocal, dtype=bool)
+        if md.frozen_idx is not None:
+            frozen[md.frozen_idx.numpy()] = True
+        assert np.array_equal(frozen, g % 5 == 0)
+        np.save(os.path.join(out_dir, f"gid{rank}.npy"), g)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_atom_migration_keeps_every_atom_once_with_its_payload(world, tmp_path):
+    mp.spawn(_migrate_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    allg = np.concatenate([np.load(tmp_path / f"gid{r}.npy") for r in range(world)])
+    assert len(allg) == 4000 and np.array_equal(np.sort(allg), np.arange(4000))
