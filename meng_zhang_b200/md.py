@@ -297,6 +297,36 @@ class DomainMD:
                                             C.c_void_p(self.f.data_ptr()), ke, s))
         self.nsteps += 1
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the step (launch-bound sizes)
+    def capture_step(self, nh: bool = False, eflag: bool = False):
+        """Capture one MD step (NVE, or Nose-Hoover when nh=True) into a CUDA graph.  A step of a few thousand atoms is
+        ~10 short kernels and is bound by launch latency, not by the GPU; replaying the captured graph issues them
+        with one call.  Valid until the next reneighbor() (buffers and list are re-created there); single rank only
+        (the NCCL halo exchange is left to eager mode)."""
+        if self.world != 1:
+            raise RuntimeError("capture_step: single-rank only")
+        fn = (lambda: self.step_nh(eflag=eflag)) if nh else (lambda: self.step(eflag=eflag))
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):              # warm-up on the capture stream: every buffer reaches its final size
+                fn()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.pair.stats()                   # collects counters: raises if the tile overflowed during warm-up
+        g = torch.cuda.CUDAGraph()
+        n0 = self.nsteps
+        with torch.cuda.graph(g, stream=side):
+            fn()                            # recorded, not executed
+        self.nsteps = n0
+        self._graph = g
+        return g
+
+    def replay(self, nsteps: int = 1):
+        for _ in range(nsteps):
+            self._graph.replay()
+        self.nsteps += nsteps
+
     # ------------------------------------------------------------------ fix nvt / fix npt (device-resident Nose-Hoover)
     def fix_nh(self, t_start, t_stop, t_damp, p_flag=(0, 0, 0), p_start=(0.0, 0.0, 0.0), p_stop=(0.0, 0.0, 0.0),
                p_damp=(1.0, 1.0, 1.0), tchain=3, pchain=3, nsteps_ramp=0):
