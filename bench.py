@@ -38,6 +38,7 @@ A_FE = 2.8553
 RC = 6.5
 SKIN = 2.0
 FLOP_TRIPLET, FLOP_PAIR, FLOP_MLP = 278.0, 168.0, 1560.0     # F_alg = 278 T + 168 N + 1560
+PUBLISHED_ATOM_STEPS_PER_S = 152880 * 1000 / 1789.44         # BASELINE.md section 1 (the reference's own 2-GPU log)
 
 
 def lattice_block(cells, origin_cells, amp, seed):
@@ -232,7 +233,13 @@ def run_ours(args):
         out = {
             "metric": "atom-steps/sec (bcc Fe ANNP)", "value": value, "unit": "atom-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak",
+            # the only speed the reference publishes for this metric, 8.55e4 atom-steps/s (whole job:
+            # its 152 880-atom deck on the authors' 2 GPUs).  Same metric, different box size and hardware; the
+            # like-for-like rerun of that deck is the `published_deck` object below.
+            "vs_baseline": value / PUBLISHED_ATOM_STEPS_PER_S,
+            "vs_baseline_note": "value / 8.55e4 atom-steps/s (annp/gpu fe_v2, 152 880 atoms, 2 GPUs, zip:log_relaxing_new.lammps:1168); see published_deck for the same deck",
+            "dtype": "f64", "data": "synthetic",
             "ns_per_day": 86400.0 * (args.steps / (ms_total * 1e-3)) * 1e-6,
             "config": {"workload": f"bcc Fe ANNP weak-scaling cell: {cells}^3 bcc cells = {nlocal} atoms per GPU, "
                                    f"{natoms_total} atoms total, NVE dt=1 fs, 300 K, skin 2 A, PBC (BASELINE configs[4])",
@@ -292,7 +299,7 @@ def run_published_deck(pot_file, device, steps=1000):
     torch.cuda.synchronize(device)
     secs = e0.elapsed_time(e1) * 1e-3
     natoms = len(x)
-    ref_value = 152880 * 1000 / 1789.44
+    ref_value = PUBLISHED_ATOM_STEPS_PER_S
     res = {"deck": "fe_st.dat 152 880 atoms, boundary m p m, fix npt temp 300 300 0.1 y 0 0 1, thermo 1, 1000 steps (zip:in.st_test)",
            "steps": steps, "seconds": secs, "atom_steps_per_s": natoms * steps / secs, "ns_per_day": 86400.0 * steps / secs * 1e-6,
            "published_atom_steps_per_s": ref_value, "published_setup": "2 MPI ranks x 2 GPUs (RTX A5000 class), LAMMPS 29Sep2021, annp/gpu fe_v2",

@@ -110,3 +110,57 @@ def test_free_boundaries_have_no_ghosts():
     x, _ = L.bcc(2, 2, 2)
     cfg = L.build_config(x + 10, np.array([50.0, 50, 50]), 6.5, periodic=(False, False, False))
     assert cfg.nghost == 0 and cfg.numneigh.max() == 15
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the Nose-Hoover host twin (tests/nh_host.py) on an analytic force field: the transcription of FixNH used to pin
+# csrc/annp_nh.cu must itself be a sound integrator (conserved extended energy, canonical temperature, relaxing stress)
+def _lj_forces(x, boxlen, eps=0.0104, sig=3.4, rc=7.5):
+    """Shifted-force Lennard-Jones (argon-like, metal units) with minimum image; returns f, pe, virial diag (W_aa)."""
+    d = x[:, None, :] - x[None, :, :]
+    d -= np.round(d / boxlen) * boxlen
+    r2 = (d * d).sum(axis=2)
+    np.fill_diagonal(r2, np.inf)
+    r = np.sqrt(r2)
+    m = r < rc
+    sr6 = np.where(m, (sig * sig / r2) ** 3, 0.0)
+    fr = np.where(m, 24.0 * eps * (2.0 * sr6 * sr6 - sr6) / r2, 0.0)            # -(dU/dr)/r
+    src6 = (sig / rc) ** 6
+    frc = 24.0 * eps * (2.0 * src6 * src6 - src6) / rc                          # -(dU/dr) at rc
+    fr = np.where(m, fr - frc / r, 0.0)
+    u = np.where(m, 4.0 * eps * (sr6 * sr6 - sr6) - 4.0 * eps * (src6 * src6 - src6) + frc * (r - rc), 0.0)
+    fvec = fr[:, :, None] * d
+    f = fvec.sum(axis=1)
+    vir = 0.5 * np.array([(d[:, :, a] * fvec[:, :, a]).sum() for a in range(3)] + [0.0, 0.0, 0.0])
+    return f, 0.5 * float(u.sum()), vir
+
+
+@pytest.mark.parametrize("p_flag", [(0, 0, 0), (0, 1, 0)], ids=["nvt", "npt_y"])
+def test_nose_hoover_host_twin_conserves_the_extended_energy(p_flag):
+    import nh_host
+    mass, dt, T = 39.948, 0.002, 40.0
+    x, box = L.fcc(3, 3, 3, a=5.31)                                               # 108 atoms, solid argon
+    n = len(x)
+    rng = np.random.default_rng(5)
+    sigma = (nh_host.BOLTZ * T / (mass * nh_host.MVV2E)) ** 0.5
+    v = rng.standard_normal((n, 3)) * sigma
+    v -= v.mean(axis=0)
+    nh = nh_host.HostNH(n, box, dt, mass, T, T, 0.2, p_flag=p_flag, p_start=(0, 0, 0), p_stop=(0, 0, 0), p_damp=(2, 2, 2))
+    f, pe, vir = _lj_forces(x, nh.boxhi - nh.boxlo)
+    nh.setup(v, vir)
+    temps, cons, ly = [], [], []
+    for step in range(4000):
+        x, v = nh.initial(x, v, f)
+        f, pe, vir = _lj_forces(x, nh.boxhi - nh.boxlo)
+        v = nh.final(v, f, vir)
+        cons.append(pe + 0.5 * nh.mvv[:3].sum() + nh.extended_energy())
+        temps.append(nh.t_current)
+        ly.append(nh.boxhi[1] - nh.boxlo[1])
+    cons = np.array(cons)
+    assert np.abs(cons - cons[0]).max() / n < 5e-6               # eV per atom over 8 ps (KE per atom is 5e-3 eV)
+    late = np.array(temps[1500:])
+    assert abs(late.mean() - T) < 4.0
+    if any(p_flag):
+        assert nh.boxhi[0] - nh.boxlo[0] == box[0] and nh.boxhi[2] - nh.boxlo[2] == box[2]    # uncoupled edges fixed
+        assert np.ptp(ly) > 1e-3                                                                # coupled edge breathes
+        assert abs(np.mean(nh.p_current[1])) < 3000.0                                           # bar, near the 0 target
