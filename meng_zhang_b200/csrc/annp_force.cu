@@ -96,13 +96,20 @@ __device__ __forceinline__ Unit make_unit(const Sched &sc, int pass, int lane) {
   return u;
 }
 
+// one out-of-line copy of pow(): inlined five times it is most of the ANNA instantiation's code and the kernel
+// stalls on instruction fetch (ncu r1b: stall_no_instruction 2.5 per issue)
+__device__ __noinline__ double anna_pow(double x, double y) { return pow(x, y); }
+
 // ANNA-ADP tail (MODE 1): the descriptor of the centre atom is in sG (raw sums).  Reference: pair_anna_adp.cpp:166-272.
 //   network -> (d2, q2); per-neighbour sums rho, mu[3], lambda[3][3], E_rep with the smooth step psi = z^4/(1+z^4),
 //   z = (r - Rc)/hc; E_i; then the i-centred pair forces with d2, q2 held fixed, written at the neighbours' list
 //   positions like the ANNP forces.  One lane per neighbour, fixed butterfly sums -> deterministic.
+//   The transcendental factors of a neighbour (three powers, three exponentials) are the same in the sum pass and in
+//   the force pass: they are computed once and parked in the shared-memory slots the ANNP backward pass would use.
 __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParams &P, const double *We, const double *Be,
                                               const double *sG, double *sH, const double2 *sA, const double2 *sB,
-                                              const double2 *sC, const int *spos, int N, int Ch, long long p0, int ii, int lane) {
+                                              double2 *sC, double2 *accA, double2 *accB, double *accC, const int *spos, int N,
+                                              int Ch, long long p0, int ii, int lane) {
 #define ROWPOS(r) ((((r) & 1) ? Ch : 0) + ((r) >> 1))
   annp_mlp_forward_warp(P, We, Be, sG, sH, lane);
   const double d2 = sH[(P.nlayers - 1) * P.nnod], q2 = sH[(P.nlayers - 1) * P.nnod + 1];
@@ -116,21 +123,28 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
   double rho = 0, mx = 0, my = 0, mz = 0, lxx = 0, lyy = 0, lzz = 0, lxy = 0, lxz = 0, lyz = 0, erep = 0;
   for (int s = lane; s < N; s += 32) {
     const int ps = ROWPOS(s);
-    const double2 A = sA[ps], B = sB[ps], Cc = sC[ps];
-    const double r = Cc.y;
+    const double2 A = sA[ps], B = sB[ps];
+    const double r = sC[ps].y;
     if (r > Rc) continue;                                          // pair_anna_adp.cpp:178 (r >= 1e-6 by the filter)
     const double x = r * A.x, y = r * A.y, z = r * B.x;
     const double sx = (r - Rc) * hcinv, sx2 = sx * sx, sx4 = sx2 * sx2;
     const double stp = sx4 / (1.0 + sx4);
-    const double u = stp * (d1 * exp(-d2 * r) + d3);
-    const double w = stp * (q1 * exp(-q2 * r) + q3);
+    const double ut = d1 * exp(-d2 * r), wt = q1 * exp(-q2 * r);
+    const double u = stp * (ut + d3);
+    const double w = stp * (wt + q3);
     mx = fma(u, x, mx); my = fma(u, y, my); mz = fma(u, z, mz);
     lxx = fma(w * x, x, lxx); lyy = fma(w * y, y, lyy); lzz = fma(w * z, z, lzz);
     lxy = fma(w * x, y, lxy); lxz = fma(w * x, z, lxz); lyz = fma(w * y, z, lyz);
     const double rz = r - r0, ez = exp(-gamma * rz);
-    rho += stp * (A0 * pow(rz, yy) * ez * (1.0 + ez) + C0);
+    const double zyy = A0 * anna_pow(rz, yy);
+    rho += stp * (zyy * ez * (1.0 + ez) + C0);
     const double pz = r / r1;
-    erep += stp * (rep_coeff * (b2 / pow(pz, b1) - b1 / pow(pz, b2)) + delta);
+    const double zb1 = anna_pow(pz, b1), zb2 = anna_pow(pz, b2);
+    erep += stp * (rep_coeff * (b2 / zb1 - b1 / zb2) + delta);
+    accA[ps] = make_double2(ut, wt);
+    accB[ps] = make_double2(ez, zyy);
+    accC[ps] = zb1;
+    sC[ps].x = zb2;                                                // dfc of the Chebyshev cutoff is not used by ANNA-ADP
   }
   rho = warp_sum(rho); mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
   lxx = warp_sum(lxx); lyy = warp_sum(lyy); lzz = warp_sum(lzz);
@@ -154,18 +168,19 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
     double fx = 0.0, fy = 0.0, fz = 0.0;
     const double x = r * A.x, y = r * A.y, z = r * B.x;
     if (!(r > Rc)) {
+      const double2 c1 = accA[ps], c2 = accB[ps];
+      const double ut = c1.x, wt = c1.y, ez = c2.x, zyy = c2.y, zb1 = accC[ps], zb2 = Cc.x;
       const double sx = (r - Rc) * hcinv, sx2 = sx * sx, sx4 = sx2 * sx2;
       const double t1 = 1.0 + sx4;
       const double stp = sx4 / t1;
       const double dstp = 4.0 * sx2 * sx / (t1 * t1) * hcinv;
-      const double rz = r - r0, ez = exp(-gamma * rz);
-      const double zyy = A0 * pow(rz, yy), gz = zyy * gamma;
+      const double rz = r - r0;
+      const double gz = zyy * gamma;
       const double drho = ez * (1.0 + ez) * (zyy * (dstp + stp * yy / rz) - gz) + C0 * dstp - gz * ez * ez;
       const double d_emb = demb * drho;
-      const double pz = r / r1, zb1 = pow(pz, b1), zb2 = pow(pz, b2);
+      const double pz = r / r1;
       const double rep_t1 = rep_coeff * (b2 / zb1 - b1 / zb2) + delta;
       const double d_rep = dstp * rep_t1 + stp * rep_coeff * ((b2 * b1 / r1) / pz * (-1.0 / zb1 + 1.0 / zb2));
-      const double ut = d1 * exp(-d2 * r), wt = q1 * exp(-q2 * r);
       const double au = stp * (ut + d3), aw = 2.0 * stp * (wt + q3);
       const double dau = dstp * (ut + d3) + stp * (-d2 * ut);
       const double daw = dstp * (wt + q3) + stp * (-q2 * wt);
@@ -416,7 +431,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     const double *We = sW + elem * P.w_per_elem;
     const double *Be = sBias + elem * P.b_per_elem;
     if constexpr (MODE == 1) {      // ANNA-ADP: forward network + ADP energy and forces, no descriptor derivatives
-      anna_adp_tail(a, P, We, Be, sG, sH, sA, sB, sC, spos, N, Ch, p0, ii, lane);
+      anna_adp_tail(a, P, We, Be, sG, sH, sA, sB, sC, accA, accB, accC, spos, N, Ch, p0, ii, lane);
       continue;
     }
 
