@@ -99,7 +99,7 @@ class DomainMD:
     """One rank's sub-domain, device resident.  `pair` is an initialised PairANNPGPU."""
 
     def __init__(self, pair, x_local, box, grid=(1, 1, 1), rank=0, device=None, type_local=None,
-                 skin=2.0, mass=55.845, dt=0.001, group=None, periodic=(True, True, True), frozen_local=None, gid_local=None):
+                 skin=2.0, mass=55.845, dt=0.001, group=None, periodic=(True, True, True), frozen_local=None, gid_local=None, list_cutoff=None):
         """periodic: per-axis `boundary p` (True) or free surface (False).  frozen_local: boolean mask of atoms held
         fixed (force and velocity zeroed every step: `fix setforce 0 0 0` on the rim of the dislocation cylinder)."""
         self.periodic = tuple(bool(p) for p in periodic)
@@ -114,7 +114,10 @@ class DomainMD:
         self.coords = rank_coords(rank, self.grid)
         self.lo = np.array([self.box[d] * self.coords[d] / self.grid[d] for d in range(3)])
         self.hi = np.array([self.box[d] * (self.coords[d] + 1) / self.grid[d] for d in range(3)])
-        self.cut = pair.cutmax
+        # list / ghost radius: what can actually interact (for the Ni copy tighter than the file's list cutoff)
+        self.cut = pair.interaction_cutoff() if hasattr(pair, "interaction_cutoff") else pair.cutmax
+        if list_cutoff is not None:
+            self.cut = float(list_cutoff)
         self.skin, self.mass, self.dt = skin, mass, dt
         self.nlocal = len(x_local)
         self.nghost = 0

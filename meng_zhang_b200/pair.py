@@ -290,6 +290,16 @@ class PairANNPGPU:
         self.handle = h
         self.cell_size = self.cutmax + self.skin           # pair_annp_gpu.cpp:222
 
+    def interaction_cutoff(self) -> float:
+        """Largest distance at which a neighbour can contribute.  Fe copies / ANNA: the pair cutoff.  Ni copy: the
+        descriptor cutoff Rc[Bohr]/1.889726 = 3.9 A, well inside the 6.5 A list cutoff LAMMPS derives from the file's
+        `Cut` field - a driver that builds its own list (md.py) can use this tighter radius; entries beyond it are
+        filtered by the kernel anyway and the order of the remaining ones is unchanged, so results are identical."""
+        p = self.params
+        if getattr(p, "sym_coerad", None) is not None and (self.variant is None or (self.variant & 0xff) == capi.VARIANT_NI):
+            return float(max(p.sym_coerad[0][2], p.sym_coeang[0][3]) / 1.889726)
+        return float(self.cutmax)
+
     def _check(self, rc):
         if rc != 0:
             msg = capi.lib().annp_b200_last_error(self.handle).decode()

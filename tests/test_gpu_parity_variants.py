@@ -154,3 +154,34 @@ def test_lammps_pair_styles_through_the_shim_driver(kind, prefix, name, ni_pot_f
         assert np.abs(out["virial"] - ref[vkey]).max() <= 1e-8
         if vflag & 4:
             assert np.abs(out["vatom"] - ref["vatom"]).max() <= 1e-9
+
+
+def test_ni_device_md_uses_the_descriptor_cutoff_for_its_list(ni_pot_file):
+    """The Ni file's `Cut` (6.5 A) only sizes LAMMPS' list; nothing beyond Rc = 7.3699 Bohr = 3.9 A contributes.  The
+    device-resident driver builds its list with the tighter radius: same forces to rounding (the surviving row entries
+    keep their order, which is what the Ni copy's forces depend on; only the lane partition of the ordered gather sums
+    changes with the row length), a third of the list entries."""
+    import torch
+    from meng_zhang_b200.md import DomainMD
+    x, box = L.fcc(5, 5, 5)
+    xp = L.perturb(x, 0.06, 17)
+    out = {}
+    for key, cut in (("tight", None), ("file", 6.5)):
+        pair = make_ni(ni_pot_file)
+        md = DomainMD(pair, xp, box, mass=58.6934, list_cutoff=cut)
+        md.reneighbor()
+        md.compute(eflag=True)
+        torch.cuda.synchronize()
+        out[key] = (md.f[: md.nlocal].cpu().numpy().copy(), float(md.engvir[0]), pair.stats().max_neigh_list, md.cut)
+        pair.clear()
+    assert abs(out["tight"][3] - 7.3699319 / 1.889726) < 1e-12 and out["file"][3] == 6.5
+    assert np.abs(out["tight"][0] - out["file"][0]).max() < 1e-13 and abs(out["tight"][1] - out["file"][1]) < 1e-11
+    assert out["tight"][2] < 0.45 * out["file"][2]
+    # and against the host path with LAMMPS' own list radius (different ghost numbering -> different row order ->
+    # the reference's order dependence shows up in the forces, not in the energy)
+    cfg = L.build_config(xp, box, 6.5)
+    pair = make_ni(ni_pot_file)
+    fh = cfg.fold(pair.compute(3, 0, cfg, ago=0))
+    assert abs(pair.eng_vdwl - out["tight"][1]) < 1e-10
+    assert np.abs(fh - out["tight"][0]).max() < 5e-2
+    pair.clear()
