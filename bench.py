@@ -286,7 +286,8 @@ def run_published_deck(pot_file, device, steps=1000):
     pair.settings([])
     pair.coeff(["*", "*", pot_file, "Fe"])
     pair.init_style()
-    md = DomainMD(pair, x, box[:, 1] - box[:, 0], device=device, skin=SKIN, mass=55.845, dt=0.001, periodic=(False, True, False))
+    md = DomainMD(pair, x, box[:, 1] - box[:, 0], device=device, skin=SKIN, mass=55.845, dt=0.001, periodic=(False, True, False),
+                  shrink_wrap=(True, False, True))
     md.set_velocities(300.0, 4928459)
     md.reneighbor()
     md.fix_nh(300.0, 300.0, 0.1, p_flag=(0, 1, 0), p_start=(0.0, 0.0, 0.0), p_stop=(0.0, 0.0, 0.0), p_damp=(1.0, 1.0, 1.0))

@@ -320,6 +320,9 @@ int annp_b200_nh_initial(annp_b200_nh nh, int nlocal, double *d_x, double *d_v, 
 int annp_b200_nh_final_kick(annp_b200_nh nh, int nlocal, double *d_v, const double *d_f, const double *d_eng_virial,
                             double *d_red12, void *stream);
 int annp_b200_nh_final_scale(annp_b200_nh nh, int nlocal, double *d_v, const double *d_red12, void *stream);
+/* new edges for dimensions the barostat does not couple (which[d] != 0): LAMMPS' shrink-wrapped `boundary m / s` faces
+ * are reset to the atoms' extent at every re-neighbouring and enter the pressure through the volume */
+int annp_b200_nh_set_box(annp_b200_nh nh, const double *lo, const double *hi, const int *which, void *stream);
 int annp_b200_nh_get_state(annp_b200_nh nh, annp_b200_nh_state *out, void *stream);   /* synchronises the stream */
 
 /* measured FP64 FMA throughput of this device in TFLOP/s (pure DFMA loop, best of reps): the

@@ -134,6 +134,7 @@ PROTOTYPES = {
     "annp_b200_nh_initial": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "annp_b200_nh_final_kick": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_nh_final_scale": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_nh_set_box": (C.c_int, [C.c_void_p, c_double_p, c_double_p, c_int_p, C.c_void_p]),
     "annp_b200_nh_get_state": (C.c_int, [C.c_void_p, C.POINTER(NhState), C.c_void_p]),
     "annp_b200_fp64_peak_tflops": (C.c_double, [C.c_void_p, C.c_int]),
     "annp_b200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),

@@ -351,6 +351,14 @@ __global__ void k_nh_scale_v(const NhState *__restrict__ st, int n, double *__re
   for (long long t = blockIdx.x * (long long) blockDim.x + threadIdx.x; t < 3LL * n; t += (long long) gridDim.x * blockDim.x) v[t] *= fe;
 }
 
+// box edges of dimensions the barostat does not couple (shrink-wrapped `boundary m/s` faces follow the atoms)
+__global__ void k_nh_set_box(NhState *st, double lo0, double lo1, double lo2, double hi0, double hi1, double hi2, int w0, int w1, int w2) {
+  const double lo[3] = {lo0, lo1, lo2}, hi[3] = {hi0, hi1, hi2};
+  const int w[3] = {w0, w1, w2};
+  for (int d = 0; d < 3; d++)
+    if (w[d] && !st->p_flag[d]) { st->boxlo[d] = lo[d]; st->boxhi[d] = hi[d]; }
+}
+
 // periodic image shifts are multiples of the box edge: they dilate with the box
 __global__ void k_nh_scale_shift(const NhState *__restrict__ st, int nsend, double *__restrict__ shift) {
   double e2[3];
@@ -498,6 +506,13 @@ int annp_b200_nh_final_scale(annp_b200_nh h, int nlocal, double *d_v, const doub
   cudaStream_t s = (cudaStream_t) stream;
   k_nh_end<<<1, 1, 0, s>>>(h->d_state, d_red12);
   if (nlocal > 0 && h->host.tstat) k_nh_scale_v<<<grid_for(3LL * nlocal, 256), 256, 0, s>>>(h->d_state, nlocal, d_v);
+  return cudaGetLastError() == cudaSuccess ? ANNP_B200_OK : ANNP_B200_ECUDA;
+}
+
+int annp_b200_nh_set_box(annp_b200_nh h, const double *lo, const double *hi, const int *which, void *stream) {
+  if (!h || !lo || !hi || !which) return ANNP_B200_EINVAL;
+  if (cudaSetDevice(h->device) != cudaSuccess) return ANNP_B200_ECUDA;
+  k_nh_set_box<<<1, 1, 0, (cudaStream_t) stream>>>(h->d_state, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], which[0], which[1], which[2]);
   return cudaGetLastError() == cudaSuccess ? ANNP_B200_OK : ANNP_B200_ECUDA;
 }
 

@@ -99,10 +99,14 @@ class DomainMD:
     """One rank's sub-domain, device resident.  `pair` is an initialised PairANNPGPU."""
 
     def __init__(self, pair, x_local, box, grid=(1, 1, 1), rank=0, device=None, type_local=None,
-                 skin=2.0, mass=55.845, dt=0.001, group=None, periodic=(True, True, True), frozen_local=None, gid_local=None, list_cutoff=None):
+                 skin=2.0, mass=55.845, dt=0.001, group=None, periodic=(True, True, True), frozen_local=None, gid_local=None, list_cutoff=None,
+                 shrink_wrap=(False, False, False)):
         """periodic: per-axis `boundary p` (True) or free surface (False).  frozen_local: boolean mask of atoms held
         fixed (force and velocity zeroed every step: `fix setforce 0 0 0` on the rim of the dislocation cylinder)."""
         self.periodic = tuple(bool(p) for p in periodic)
+        # LAMMPS `boundary m` on a free-surface axis: the box edge follows the atoms' extent at every re-neighbouring
+        # (never inside the initial box) and enters the pressure through the volume
+        self.shrink_wrap = tuple(bool(w) and not self.periodic[d] for d, w in enumerate(shrink_wrap))
         self.pair = pair
         self.L = capi.lib()
         self.h = pair.handle
@@ -130,6 +134,9 @@ class DomainMD:
         self.x = self.f = self.type = None
         self.nsteps = 0
         self.box_origin = np.zeros(3)
+        self.box_min_lo, self.box_min_hi = np.zeros(3), self.box.copy()      # data-file box: the shrink-wrap minimum
+        self.wrap_lo, self.wrap_hi = np.zeros(3), self.box.copy()
+        self.nh = None
         # global atom ids (travel with the atoms when they migrate); default: rank-concatenated numbering
         self.gid = None if gid_local is None else torch.as_tensor(np.ascontiguousarray(gid_local), dtype=torch.int64, device=self.dev)
         self.migrated = 0
@@ -202,6 +209,24 @@ class DomainMD:
         self.gid = got[:, 11].to(torch.int64).contiguous()
         return got[:, 0:3].contiguous(), got[:, 6:9].contiguous()
 
+    def _shrink_wrap_box(self, xl):
+        from .lammps_compat import shrink_wrap
+        ext = torch.stack([xl.amin(dim=0), xl.amax(dim=0)]) if xl.shape[0] else torch.zeros((2, 3), dtype=torch.float64, device=self.dev)
+        ext[0] = -ext[0]
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ext, op=dist.ReduceOp.MAX, group=self.group)
+        ext = ext.cpu().numpy()
+        which = np.zeros(3, dtype=np.int32)
+        for d in range(3):
+            if self.shrink_wrap[d]:
+                self.wrap_lo[d], self.wrap_hi[d] = shrink_wrap(self.box_min_lo[d], self.box_min_hi[d], -ext[0, d], ext[1, d])
+                which[d] = 1
+        if self.nh is not None:
+            lo, hi = self.wrap_lo.copy(), self.wrap_hi.copy()
+            self._nh_ck(self.L.annp_b200_nh_set_box(self.nh, lo.ctypes.data_as(capi.c_double_p), hi.ctypes.data_as(capi.c_double_p),
+                                                    which.ctypes.data_as(capi.c_int_p), self._stream()))
+
     def reneighbor(self):
         """Migrate atoms, rebuild send lists, ghosts and the device neighbour list from the current local positions."""
         xl = (self.x[: self.nlocal] if self.x is not None else self._x_local0)
@@ -209,6 +234,8 @@ class DomainMD:
         xl, fl = self._migrate(xl, fl)
         xl_host = xl.cpu().numpy()
         cutghost = self.cut + self.skin
+        if any(self.shrink_wrap):
+            self._shrink_wrap_box(xl)
         idx, shift, send_counts = build_send_lists(xl_host, self.lo, self.hi, self.box, self.grid, self.coords, cutghost, self.periodic)
         self.send_counts = [int(c) for c in send_counts]
         if self.world > 1:
@@ -350,6 +377,9 @@ class DomainMD:
         cfg.tdof = 0.0
         cfg.nsteps_ramp = nsteps_ramp
         lo, hi = np.zeros(3), self.box.astype(np.float64).copy()
+        for d in range(3):
+            if self.shrink_wrap[d]:
+                lo[d], hi[d] = self.wrap_lo[d], self.wrap_hi[d]
         err = C.create_string_buffer(256)
         h = C.c_void_p(None)
         rc = self.L.annp_b200_nh_create(C.byref(cfg), lo.ctypes.data_as(capi.c_double_p), hi.ctypes.data_as(capi.c_double_p),
@@ -377,12 +407,14 @@ class DomainMD:
             import torch.distributed as dist
             dist.all_reduce(self.red12, group=self.group)
 
-    def step_nh(self, eflag=False):
-        """One step of FixNH::initial_integrate, force, FixNH::final_integrate."""
+    def _nh_initial(self):
         s = self._stream()
         shift = C.c_void_p(self.send_shift.data_ptr()) if self.nsend > 0 else None
         self._nh_ck(self.L.annp_b200_nh_initial(self.nh, self.nlocal, C.c_void_p(self.x.data_ptr()), C.c_void_p(self.v.data_ptr()),
                                                 C.c_void_p(self.f.data_ptr()), self.nsend, shift, s))
+
+    def _nh_final(self, eflag):
+        s = self._stream()
         self.compute(eflag=eflag, vflag=True)
         self._nh_ck(self.L.annp_b200_nh_final_kick(self.nh, self.nlocal, C.c_void_p(self.v.data_ptr()), C.c_void_p(self.f.data_ptr()),
                                                    C.c_void_p(self.engvir.data_ptr()), C.c_void_p(self.red12.data_ptr()), s))
@@ -390,10 +422,19 @@ class DomainMD:
         self._nh_ck(self.L.annp_b200_nh_final_scale(self.nh, self.nlocal, C.c_void_p(self.v.data_ptr()), C.c_void_p(self.red12.data_ptr()), s))
         self.nsteps += 1
 
+    def step_nh(self, eflag=False):
+        """One step of FixNH::initial_integrate, force, FixNH::final_integrate."""
+        self._nh_initial()
+        self._nh_final(eflag)
+
     def nh_state(self):
         st = capi.NhState()
         self._nh_ck(self.L.annp_b200_nh_get_state(self.nh, C.byref(st), self._stream()))
         return st
+
+    def _nh_box_corners(self):
+        st = self.nh_state()
+        return np.array(st.boxlo[:]), np.array(st.boxhi[:])
 
     def sync_box_from_nh(self):
         """After npt steps the box lives in the thermostat state: refresh the host copy (needed to re-neighbour)."""
@@ -406,25 +447,37 @@ class DomainMD:
         return st
 
     def run_nh(self, nsteps: int, check_every: int = 5, thermo_every: int = 0):
-        """`run nsteps` under fix nvt / npt with the deck's re-neighbouring rule.  Returns
-        [(step, pe, ke, extended_energy, T, (pxx, pyy, pzz), box[3])] at the thermo steps."""
+        """`run nsteps` under fix nvt / npt with the deck's `neigh_modify every 5 delay 5 check yes` rule, in the order of
+        LAMMPS' Verlet::run: initial_integrate, neighbour decision on the new positions, force, final_integrate.
+        Returns [(step, pe, ke, extended_energy, T, (pxx, pyy, pzz), box[3])] at the thermo steps; the pressures are
+        LAMMPS' thermo values, (m v(x)v + virial) / V from the velocities at the END of the step."""
         x_ref = self.x[: self.nlocal].clone()
+        box_ref = self._nh_box_corners()
         out, self.rebuilds = [], 0
+        nktv2p = 1.6021765e6
         for n in range(1, nsteps + 1):
             want = thermo_every > 0 and (n % thermo_every == 0 or n == nsteps)
+            self._nh_initial()
             if check_every > 0 and n % check_every == 0:
-                # the deck's criterion on the displacement since the last build (box dilation included)
                 moved = (self.x[: self.nlocal] - x_ref).square().sum(dim=1).max()
                 if self.world > 1:
                     import torch.distributed as dist
                     dist.all_reduce(moved, op=dist.ReduceOp.MAX, group=self.group)
-                if float(moved) > (0.5 * self.skin) ** 2:
+                trigger = 0.5 * self.skin
+                if self.nh_pstat:
+                    # Neighbor::check_distance with a changing box: the skin is reduced by the displacement of the two
+                    # box corners since the last build, delta = (skin - (d_lo + d_hi)) / 2
+                    st = self.nh_state()
+                    lo_now, hi_now = np.array(st.boxlo[:]), np.array(st.boxhi[:])
+                    trigger = 0.5 * (self.skin - (np.linalg.norm(lo_now - box_ref[0]) + np.linalg.norm(hi_now - box_ref[1])))
+                if trigger <= 0.0 or float(moved) > trigger ** 2:
                     if self.nh_pstat:
                         self.sync_box_from_nh()
                     self.reneighbor()
                     x_ref = self.x[: self.nlocal].clone()
+                    box_ref = self._nh_box_corners()
                     self.rebuilds += 1
-            self.step_nh(eflag=want)
+            self._nh_final(want)
             if want:
                 st = self.nh_state()
                 pe = self.engvir[:1].clone()
@@ -432,8 +485,10 @@ class DomainMD:
                     import torch.distributed as dist
                     dist.all_reduce(pe, group=self.group)
                 ke = 0.5 * (st.ke_tensor[0] + st.ke_tensor[1] + st.ke_tensor[2])
-                out.append((self.nsteps, float(pe), ke, st.extended_energy, st.t_current, tuple(st.p_current[:]),
-                            tuple(st.boxhi[d] - st.boxlo[d] for d in range(3))))
+                box = tuple(st.boxhi[d] - st.boxlo[d] for d in range(3))
+                vol = box[0] * box[1] * box[2]
+                p = tuple((st.ke_tensor[d] + st.virial[d]) / vol * nktv2p for d in range(3))
+                out.append((self.nsteps, float(pe), ke, st.extended_energy, st.t_current, p, box))
         return out
 
     def thermo(self):

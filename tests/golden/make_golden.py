@@ -194,6 +194,32 @@ def dump_kind(kind, prefix, potfile, cases_fn):
               f"fmax {np.abs(cfg.fold(r1['f'])).max():.6e} ({r1['seconds']:.1f} s)")
 
 
+def dump_fe_st_log():
+    """Thermo table of the reference's own published run (numbers only): 1 001 rows of
+    Step Temp PotEng KinEng Lx Ly Lz Press Volume Pxx Pyy Pzz from log_relaxing_{new,old}.lammps, plus the minimiser
+    summary (energies, force norms, line-search alpha) that precedes it."""
+    z = zipfile.ZipFile(f"{REF}/annp-gpu-lammps/fe_v2/performance test.zip")
+    out = {}
+    for name in ("new", "old"):
+        t = z.read(f"performance comparsion/log_relaxing_{name}.lammps").decode().splitlines()
+        i0 = [i for i, l in enumerate(t) if l.startswith("Step Temp PotEng")][0]
+        rows = []
+        for l in t[i0 + 1:]:
+            p = l.split()
+            if len(p) != 12:
+                break
+            rows.append([float(v) for v in p])
+        out[f"thermo_{name}"] = np.array(rows)
+        assert out[f"thermo_{name}"].shape == (1001, 12)
+    out["columns"] = np.array("Step Temp PotEng KinEng Lx Ly Lz Press Volume Pxx Pyy Pzz".split())
+    out["min_energy_initial_final_new"] = np.array([-684876292.365723, -684876369.462402])      # log_relaxing_new.lammps:117
+    out["min_fnorm_initial_final_new"] = np.array([39.623051, 19.978295])                        # :118
+    out["min_fmax_initial_final_new"] = np.array([0.93490135, 0.52800152])                       # :119
+    out["min_alpha_maxmove_new"] = np.array([0.10696316, 0.056476709])                           # :120
+    np.savez_compressed(os.path.join(OUT, "fe_st_log.npz"), **out)
+    print("fe_st_log:", out["thermo_new"][0], out["thermo_new"][-1][:6])
+
+
 def dump_structures():
     """Atoms written by the reference's own structure generators (oracle/_ref/gen_screw, gen_stgb)."""
     import subprocess
@@ -230,6 +256,9 @@ def dump_structures():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "log":
+        dump_fe_st_log()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "structures":
         dump_structures()
         sys.exit(0)
@@ -243,5 +272,6 @@ if __name__ == "__main__":
     dump_kind("annp_ni", "annp_ni", NI_POT, ni_cases)
     dump_kind("anna_adp", "anna_adp", ANNA_POT, anna_cases)
     dump_structures()
+    dump_fe_st_log()
     dump_fe_st()
     dump_cases()
