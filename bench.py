@@ -272,43 +272,27 @@ def run_ours(args):
 
 def run_published_deck(pot_file, device, steps=1000):
     """The one run the reference publishes a speed for: its own 152 880-atom bcc-Fe slab fe_st.dat,
-    `boundary m p m`, `fix npt temp 300 300 0.1 y 0 0 1`, dt 1 fs, thermo every step, 1 000 steps - 1 789.44 s on the
-    authors' 2 GPUs = 8.55e4 atom-steps/s (log_relaxing_new.lammps:1168-1176).  Same deck here on ONE B200, device
-    resident (the deck's 1-iteration minimisation is skipped; positions are the data file's)."""
-    import torch
-    import util
-    from meng_zhang_b200.md import DomainMD
-    from meng_zhang_b200.pair import PairANNPGPU
-    z = np.load(os.path.join(util.GOLDEN, "fe_st.npz"))
-    box = z["box"]
-    x = z["x"] - box[:, 0]
-    pair = PairANNPGPU(ntypes=1, device=device.index, skin=SKIN)
-    pair.settings([])
-    pair.coeff(["*", "*", pot_file, "Fe"])
-    pair.init_style()
-    md = DomainMD(pair, x, box[:, 1] - box[:, 0], device=device, skin=SKIN, mass=55.845, dt=0.001, periodic=(False, True, False),
-                  shrink_wrap=(True, False, True))
-    md.set_velocities(300.0, 4928459)
-    md.reneighbor()
-    md.fix_nh(300.0, 300.0, 0.1, p_flag=(0, 1, 0), p_start=(0.0, 0.0, 0.0), p_stop=(0.0, 0.0, 0.0), p_damp=(1.0, 1.0, 1.0))
-    md.run_nh(20, thermo_every=1)
-    torch.cuda.synchronize(device)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    out = md.run_nh(steps, thermo_every=1)
-    e1.record()
-    torch.cuda.synchronize(device)
-    secs = e0.elapsed_time(e1) * 1e-3
-    natoms = len(x)
-    ref_value = PUBLISHED_ATOM_STEPS_PER_S
-    res = {"deck": "fe_st.dat 152 880 atoms, boundary m p m, fix npt temp 300 300 0.1 y 0 0 1, thermo 1, 1000 steps (zip:in.st_test)",
-           "steps": steps, "seconds": secs, "atom_steps_per_s": natoms * steps / secs, "ns_per_day": 86400.0 * steps / secs * 1e-6,
-           "published_atom_steps_per_s": ref_value, "published_setup": "2 MPI ranks x 2 GPUs (RTX A5000 class), LAMMPS 29Sep2021, annp/gpu fe_v2",
-           "ratio_vs_published": natoms * steps / secs / ref_value, "rebuilds": md.rebuilds,
-           "T_final": out[-1][4], "pyy_final_bar": out[-1][5][1], "ly_final": out[-1][6][1],
-           "published_step1000": "see zip:log_relaxing_new.lammps (T, Ly, Pyy columns)"}
-    pair.clear()
-    return res
+    `boundary m p m`, one cg minimiser iteration, `velocity all create 300 4928459`, `fix npt temp 300 300 0.1 y 0 0 1`,
+    dt 1 fs, thermo every step, 1 000 steps - loop time 1 789.44 s on the authors' 2 GPUs = 8.55e4 atom-steps/s
+    (log_relaxing_new.lammps:1168-1176).  scripts/replay_published_deck.py replays that deck on ONE B200, device
+    resident, and the thermo columns land on the log's to its printed precision; the timed region is LAMMPS' "Loop
+    time" region (the 1 000 steps incl. per-step thermo, without setup and minimisation)."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import replay_published_deck as R
+    ours, ref, mini, log, rebuilds = R.replay(steps=steps, device_index=device.index)
+    secs = mini["loop_seconds"]
+    natoms = 152880
+    col = {str(c): i for i, c in enumerate(log["columns"])}
+    return {"deck": "fe_st.dat 152 880 atoms, boundary m p m, cg minimiser step, velocity create 300 4928459, fix npt temp 300 300 0.1 y 0 0 1, "
+                    "thermo 1, 1000 steps (zip:in.st_test)",
+            "steps": steps, "seconds": secs, "atom_steps_per_s": natoms * steps / secs, "ns_per_day": 86400.0 * steps / secs * 1e-6,
+            "published_atom_steps_per_s": PUBLISHED_ATOM_STEPS_PER_S, "published_seconds": 1789.44,
+            "published_setup": "2 MPI ranks x 2 GPUs (RTX A5000 class), LAMMPS 29Sep2021, annp/gpu fe_v2",
+            "ratio_vs_published": natoms * steps / secs / PUBLISHED_ATOM_STEPS_PER_S, "rebuilds": rebuilds,
+            "T_final": float(ours[-1, col["Temp"]]), "T_final_log": float(ref[-1, col["Temp"]]),
+            "Ly_final": float(ours[-1, col["Ly"]]), "Ly_final_log": float(ref[-1, col["Ly"]]),
+            "Press_final_bar": float(ours[-1, col["Press"]]), "Press_final_log_bar": float(ref[-1, col["Press"]]),
+            "max_rel_dT_over_run": float(np.abs(ours[:, col["Temp"]] / ref[:, col["Temp"]] - 1.0).max())}
 
 
 def split_config(cfg, nparts):

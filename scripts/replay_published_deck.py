@@ -27,13 +27,13 @@ from meng_zhang_b200.md import DomainMD  # noqa: E402
 from meng_zhang_b200.pair import PairANNPGPU  # noqa: E402
 
 
-def replay(steps=1000):
+def replay(steps=1000, device_index=None):
     z = np.load(os.path.join(util.GOLDEN, "fe_st.npz"))
     log = np.load(os.path.join(util.GOLDEN, "fe_st_log.npz"))
     box = z["box"]
     x0 = z["x"] - box[:, 0]                                         # atoms in ID order
     n = len(x0)
-    pair = PairANNPGPU(ntypes=1)
+    pair = PairANNPGPU(ntypes=1, device=-1 if device_index is None else device_index)
     pair.settings([])
     pair.coeff(["*", "*", util.write_fe_potential("/tmp/annp_b200_replay_fe.ann"), "Fe"])
     pair.init_style()
@@ -73,8 +73,14 @@ def replay(steps=1000):
     vol0 = b0[0] * b0[1] * b0[2]
     p0 = [(st.ke_tensor[d] + st.virial[d]) / vol0 * nk for d in range(3)]
     rows = [[0, st.t_current, float(md.engvir[0]), 0.5 * sum(st.ke_tensor[:3]), *b0, sum(p0) / 3.0, vol0, *p0]]
-    for s, pe, ke, ext, T, p, b in md.run_nh(steps, check_every=5, thermo_every=1):
+    torch.cuda.synchronize(md.dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for s, pe, ke, ext, T, p, b in md.run_nh(steps, check_every=5, thermo_every=1):      # LAMMPS' "Loop time" region
         rows.append([s, T, pe, ke, *b, sum(p) / 3.0, b[0] * b[1] * b[2], *p])
+    ev1.record()
+    torch.cuda.synchronize(md.dev)
+    mini["loop_seconds"] = ev0.elapsed_time(ev1) * 1e-3
     ours = np.array(rows)
     ref = log["thermo_new"][: len(ours)]
     pair.clear()
