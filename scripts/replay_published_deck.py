@@ -28,51 +28,86 @@ from meng_zhang_b200.pair import PairANNPGPU  # noqa: E402
 
 
 def replay(steps=1000, device_index=None):
+    """Returns (ours[steps+1,12], log[steps+1,12], minimiser summary, log arrays, rebuilds).  Under torch.distributed
+    (one rank per GPU, as the reference's `processors 2 1 1`) the slab is brick-decomposed; every rank returns the same
+    (all-reduced) thermo table."""
+    import torch.distributed as dist
+    from meng_zhang_b200.md import decompose, rank_coords
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        device_index = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(device_index)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", device_index))
+    grid = decompose(world)
     z = np.load(os.path.join(util.GOLDEN, "fe_st.npz"))
     log = np.load(os.path.join(util.GOLDEN, "fe_st_log.npz"))
     box = z["box"]
-    x0 = z["x"] - box[:, 0]                                         # atoms in ID order
+    boxlen = box[:, 1] - box[:, 0]
+    x_all = z["x"] - box[:, 0]                                      # atoms in ID order
+    n_all = len(x_all)
+    # brick ownership as md._migrate assigns it (outermost bricks own what lies beyond a free face)
+    cell = np.floor(x_all / (boxlen / np.array(grid))).astype(np.int64)
+    cell = np.clip(cell, 0, np.array(grid) - 1)
+    owner = cell[:, 0] + cell[:, 1] * grid[0] + cell[:, 2] * grid[0] * grid[1]
+    gid = np.nonzero(owner == rank)[0]
+    x0 = x_all[gid]
     n = len(x0)
     pair = PairANNPGPU(ntypes=1, device=-1 if device_index is None else device_index)
     pair.settings([])
-    pair.coeff(["*", "*", util.write_fe_potential("/tmp/annp_b200_replay_fe.ann"), "Fe"])
+    pair.coeff(["*", "*", util.write_fe_potential(f"/tmp/annp_b200_replay_fe_{rank}.ann"), "Fe"])
     pair.init_style()
-    kw = dict(mass=55.845, dt=0.001, periodic=(False, True, False), shrink_wrap=(True, False, True))
+    kw = dict(mass=55.845, dt=0.001, periodic=(False, True, False), shrink_wrap=(True, False, True), grid=grid, rank=rank,
+              device=None if device_index is None else torch.device("cuda", device_index), gid_local=gid)
+
+    def gsum(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        return float(t)
+
+    def gmax(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    def evaluate(xl):
+        md = DomainMD(pair, xl, boxlen, **kw)
+        md.reneighbor()
+        md.compute(eflag=True, vflag=True)
+        assert np.array_equal(md.gid.cpu().numpy(), gid)            # nobody migrates at the first build
+        return md, md.f[:n].cpu().numpy(), gsum(md.engvir[0])
+
     # ---- minimize: ONE cg iteration = one quadratic line search along h = f (min_linesearch.cpp, linemin_quadratic):
     # trial step alpha = dmax / max|h| (dmax = 0.1), then the secant root of the directional derivative,
     # alpha0 = alpha - alpha * fh / (fh - fh_prev) with fh = f(x + alpha h).h, is taken when the quadratic model holds
     # (relerr <= 1e-3): two force evaluations, as the log reports.  The log's "alpha" is the trial value.
-    md = DomainMD(pair, x0, box[:, 1] - box[:, 0], **kw)
-    md.reneighbor()
-    md.compute(eflag=True, vflag=True)
-    f0 = md.f[:n].cpu().numpy()
-    e0 = float(md.engvir[0])
-    alpha = 0.1 / np.abs(f0).max()
-    md = DomainMD(pair, x0 + alpha * f0, box[:, 1] - box[:, 0], **kw)
-    md.reneighbor()
-    md.compute(eflag=True, vflag=True)
-    ft = md.f[:n].cpu().numpy()
-    et = float(md.engvir[0])
-    fh_prev, fh = float((f0 * f0).sum()), float((ft * f0).sum())
+    _, f0, e0 = evaluate(x0)
+    fmax0 = gmax(np.abs(f0).max())
+    alpha = 0.1 / fmax0
+    _, ft, et = evaluate(x0 + alpha * f0)
+    fh_prev, fh = gsum((f0 * f0).sum()), gsum((ft * f0).sum())
     relerr = abs(1.0 - (0.5 * alpha * (fh + fh_prev) + et) / e0)
     alpha0 = alpha - alpha * fh / (fh - fh_prev)
     assert relerr <= 1.0e-3 and 0.0 < alpha0 < 1.0
-    mini = {"energy_initial": e0, "fnorm_initial": float(np.linalg.norm(f0)), "fmax_initial": float(np.abs(f0).max()), "alpha_trial": float(alpha),
-            "alpha_quadratic": float(alpha0), "energy_trial": et}
-    x1 = x0 + alpha0 * f0
-    md = DomainMD(pair, x1, box[:, 1] - box[:, 0], **kw)
-    md.v = torch.as_tensor(velocity_create(n, 55.845, 300.0, 4928459), dtype=torch.float64, device=md.dev)
+    mini = {"energy_initial": e0, "fnorm_initial": fh_prev ** 0.5, "fmax_initial": fmax0, "alpha_trial": float(alpha),
+            "alpha_quadratic": float(alpha0), "energy_trial": et, "n_gpus": world}
+    md = DomainMD(pair, x0 + alpha0 * f0, boxlen, **kw)
+    md.v = torch.as_tensor(velocity_create(n_all, 55.845, 300.0, 4928459)[gid], dtype=torch.float64, device=md.dev)
     md.reneighbor()
     md.fix_nh(300.0, 300.0, 0.1, p_flag=(0, 1, 0), p_start=(0.0,) * 3, p_stop=(0.0,) * 3, p_damp=(1.0,) * 3)
-    f1 = md.f[:n].cpu().numpy()
-    mini.update({"energy_final": float(md.engvir[0]), "fnorm_final": float(np.linalg.norm(f1)), "fmax_final": float(np.abs(f1).max()),
-                 "max_atom_move_as_logged": float(alpha * np.abs(f1).max())})
+    f1 = md.f[: md.nlocal].cpu().numpy()
+    fmax1 = gmax(np.abs(f1).max())
+    pe0 = gsum(md.engvir[0])
+    mini.update({"energy_final": pe0, "fnorm_final": gsum((f1 * f1).sum()) ** 0.5, "fmax_final": fmax1,
+                 "max_atom_move_as_logged": float(alpha * fmax1)})
     st = md.nh_state()
     nk = 1.6021765e6
     b0 = [st.boxhi[d] - st.boxlo[d] for d in range(3)]
     vol0 = b0[0] * b0[1] * b0[2]
     p0 = [(st.ke_tensor[d] + st.virial[d]) / vol0 * nk for d in range(3)]
-    rows = [[0, st.t_current, float(md.engvir[0]), 0.5 * sum(st.ke_tensor[:3]), *b0, sum(p0) / 3.0, vol0, *p0]]
+    rows = [[0, st.t_current, pe0, 0.5 * sum(st.ke_tensor[:3]), *b0, sum(p0) / 3.0, vol0, *p0]]
     torch.cuda.synchronize(md.dev)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -80,7 +115,7 @@ def replay(steps=1000, device_index=None):
         rows.append([s, T, pe, ke, *b, sum(p) / 3.0, b[0] * b[1] * b[2], *p])
     ev1.record()
     torch.cuda.synchronize(md.dev)
-    mini["loop_seconds"] = ev0.elapsed_time(ev1) * 1e-3
+    mini["loop_seconds"] = gmax(ev0.elapsed_time(ev1) * 1e-3)
     ours = np.array(rows)
     ref = log["thermo_new"][: len(ours)]
     pair.clear()
@@ -105,6 +140,10 @@ def main():
         res[name] = {"max_rel_dT": rel(1, sl), "max_rel_dKinEng": rel(3, sl), "max_abs_dLx": absd(4, sl), "max_abs_dLy": absd(5, sl), "max_abs_dLz": absd(6, sl),
                      "max_abs_dPress_bar": absd(7, sl), "max_abs_dPyy_bar": absd(10, sl), "max_rel_dVolume": rel(8, sl),
                      "max_abs_dPotEng_eV": absd(2, sl)}
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    res["loop_seconds"] = mini["loop_seconds"]
+    res["atom_steps_per_s"] = 152880 * a.steps / mini["loop_seconds"]
     print(json.dumps(res, indent=1))
     if a.out:
         with open(a.out, "w") as fp:
