@@ -227,11 +227,14 @@ class DomainMD:
             self._nh_ck(self.L.annp_b200_nh_set_box(self.nh, lo.ctypes.data_as(capi.c_double_p), hi.ctypes.data_as(capi.c_double_p),
                                                     which.ctypes.data_as(capi.c_int_p), self._stream()))
 
-    def reneighbor(self):
-        """Migrate atoms, rebuild send lists, ghosts and the device neighbour list from the current local positions."""
+    def reneighbor(self, migrate: bool = True):
+        """Migrate atoms, rebuild send lists, ghosts and the device neighbour list from the current local positions.
+        migrate=False keeps every atom on its rank, unwrapped and in place (used inside a line search, where the
+        minimiser's direction vectors must stay aligned with the atoms)."""
         xl = (self.x[: self.nlocal] if self.x is not None else self._x_local0)
         fl = self.f[: self.nlocal] if self.f is not None else torch.zeros_like(xl)
-        xl, fl = self._migrate(xl, fl)
+        if migrate or self.gid is None:
+            xl, fl = self._migrate(xl, fl)
         xl_host = xl.cpu().numpy()
         cutghost = self.cut + self.skin
         if any(self.shrink_wrap):
@@ -326,6 +329,127 @@ class DomainMD:
         self._ck(self.L.annp_b200_nve_final(self.h, self.nlocal, self.dt, self.mass, C.c_void_p(self.v.data_ptr()),
                                             C.c_void_p(self.f.data_ptr()), ke, s))
         self.nsteps += 1
+
+    # ------------------------------------------------------------------ `minimize etol ftol maxiter maxeval` (min_style cg)
+    def minimize(self, etol: float, ftol: float, maxiter: int, maxeval: int, dmax: float = 0.1):
+        """LAMMPS' default minimiser, restated: Polak-Ribiere conjugate gradients (MinCG::iterate) with the quadratic
+        line search of MinLineSearch::linemin_quadratic (trial step alpha = min(1, dmax / max|h|), secant projection of
+        the directional derivative when the quadratic model holds, else backtracking with slope 0.4), metal units
+        (thermo norm no).  Vectors live on the device; only dot products come to the host.  The neighbour list is
+        re-checked at every evaluation as LAMMPS does during minimisation (`every 1 delay 0 check yes`).
+        Returns a dict like LAMMPS' "Minimization stats"."""
+        ALPHA_MAX, ALPHA_REDUCE, BACKTRACK_SLOPE, QUADRATIC_TOL, EMACH, EPS_QUAD, EPS_ENERGY = 1.0, 0.5, 0.4, 0.1, 1.0e-8, 1.0e-28, 1.0e-8
+        if self.x is None:
+            self.reneighbor()
+        n = self.nlocal
+        self._min_xref = self.x[:n].clone()
+
+        def gsum(t):
+            t = t.reshape(1).clone()
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(t, group=self.group)
+            return float(t)
+
+        def gmax(t):
+            t = t.reshape(1).clone()
+            if self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            return float(t)
+
+        def energy_force():
+            moved = gmax((self.x[:n] - self._min_xref).square().sum(dim=1).max()) if n else 0.0
+            if moved > (0.5 * self.skin) ** 2:
+                self.reneighbor(migrate=False)
+                self._min_xref = self.x[:n].clone()
+            self.compute(eflag=True)
+            return gsum(self.engvir[0])
+
+        stats = {"evaluations": 0, "iterations": 0}
+        ecurrent = energy_force()
+        einitial = ecurrent
+        f = lambda: self.f[:n]
+        h = f().clone()
+        g = f().clone()
+        gg = gsum((g * g).sum())
+        stats["fnorm_initial"], stats["fmax_initial"] = gg ** 0.5, gmax(f().abs().max())
+        stop, alpha_final, enext_to_last = "max iterations", 0.0, ecurrent
+
+        def linemin(eoriginal):
+            nonlocal ecurrent
+            fdothall = gsum((f() * h).sum())
+            if fdothall <= 0.0:
+                return "search direction is not downhill", 0.0
+            hmaxall = gmax(h.abs().max())
+            if hmaxall == 0.0:
+                return "forces are zero", 0.0
+            alphamax = min(ALPHA_MAX, dmax / hmaxall)
+            x0 = self.x[:n].clone()
+
+            def alpha_step(a):
+                self.x[:n] = x0 + a * h
+                stats["evaluations"] += 1
+                return energy_force()
+
+            alpha, fhprev, engprev, alphaprev = alphamax, fdothall, eoriginal, 0.0
+            while True:
+                ecurrent = alpha_step(alpha)
+                fh = gsum((f() * h).sum())
+                delfh = fh - fhprev
+                if abs(fh) < EPS_QUAD or abs(delfh) < EPS_QUAD:
+                    self.x[:n] = x0
+                    ecurrent = energy_force()
+                    return "linesearch alpha is zero (quadratic factors)", 0.0
+                relerr = abs(1.0 - (0.5 * (alpha - alphaprev) * (fh + fhprev) + ecurrent) / engprev)
+                alpha0 = alpha - (alpha - alphaprev) * fh / delfh
+                if relerr <= QUADRATIC_TOL and 0.0 < alpha0 < ALPHA_MAX:
+                    ecurrent = alpha_step(alpha0)
+                    if ecurrent - eoriginal < EMACH:
+                        return None, alpha            # LAMMPS reports the trial alpha, the atoms sit at alpha0
+                de_ideal = -BACKTRACK_SLOPE * alpha * fdothall
+                de = ecurrent - eoriginal
+                if de <= de_ideal:
+                    return None, alpha
+                fhprev, engprev, alphaprev = fh, ecurrent, alpha
+                alpha *= ALPHA_REDUCE
+                if alpha <= 0.0 or de_ideal >= -EMACH:
+                    self.x[:n] = x0
+                    ecurrent = energy_force()
+                    return "linesearch alpha is zero", 0.0
+
+        ndof = 3.0 * gsum(torch.tensor(float(n), dtype=torch.float64, device=self.dev))
+        for it in range(maxiter):
+            stats["iterations"] += 1
+            eprevious = ecurrent
+            enext_to_last = eprevious
+            fail, alpha_final = linemin(ecurrent)
+            if fail:
+                stop = fail
+                break
+            if stats["evaluations"] >= maxeval:
+                stop = "max force evaluations"
+                break
+            if abs(ecurrent - eprevious) < etol * 0.5 * (abs(ecurrent) + abs(eprevious) + EPS_ENERGY):
+                stop = "energy tolerance"
+                break
+            ff, fg = gsum((f() * f()).sum()), gsum((f() * g).sum())
+            if ftol > 0.0 and ff < ftol * ftol:
+                stop = "force tolerance"
+                break
+            beta = max(0.0, (ff - fg) / gg)
+            if (stats["iterations"] + 1) % int(min(2 ** 31 - 1, ndof)) == 0:
+                beta = 0.0
+            gg = ff
+            g = f().clone()
+            h = g + beta * h
+            if gsum((g * h).sum()) <= 0.0:
+                h = g.clone()
+        ffin = f()
+        stats.update({"stopping_criterion": stop, "energy_initial": einitial, "energy_next_to_last": enext_to_last, "energy_final": ecurrent,
+                      "fnorm_final": gsum((ffin * ffin).sum()) ** 0.5, "fmax_final": gmax(ffin.abs().max()), "alpha_final": alpha_final,
+                      "max_atom_move": alpha_final * gmax(ffin.abs().max())})
+        return stats
 
     # ------------------------------------------------------------------ CUDA-graph replay of the step (launch-bound sizes)
     def capture_step(self, nh: bool = False, eflag: bool = False):

@@ -116,9 +116,14 @@ def test_replay_of_the_references_published_run_matches_its_lammps_log():
     import replay_published_deck as R
     ours, ref, mini, log, rebuilds = R.replay(steps=120)
     # minimiser summary (log_relaxing_new.lammps:117-120); the reference's GPU build is mixed precision (2e-5 eV/A)
+    assert mini["iterations"] == 1 and mini["evaluations"] == 2 and mini["stopping_criterion"] == "energy tolerance"
     assert abs(mini["fnorm_final"] - float(log["min_fnorm_initial_final_new"][1])) < 2e-4
     assert abs(mini["fmax_final"] - float(log["min_fmax_initial_final_new"][1])) < 5e-5
-    assert abs(mini["alpha_trial"] - float(log["min_alpha_maxmove_new"][0])) < 5e-6
+    assert abs(mini["alpha_final"] - float(log["min_alpha_maxmove_new"][0])) < 5e-6
+    assert abs(mini["max_atom_move"] - float(log["min_alpha_maxmove_new"][1])) < 5e-6
+    # energies: the reference's GPU build carries ~5e-9 relative error (3.4 eV at step 0, 7.1 eV after the step)
+    for ours_e, log_e in zip((mini["energy_initial"], mini["energy_final"]), log["min_energy_initial_final_new"]):
+        assert abs(ours_e / float(log_e) - 1.0) < 2e-8
     col = {c: i for i, c in enumerate(str(c) for c in log["columns"])}
     T, Tl = ours[:, col["Temp"]], ref[:, col["Temp"]]
     assert np.abs(T[:21] / Tl[:21] - 1.0).max() < 2e-6 and np.abs(T / Tl - 1.0).max() < 1e-5
@@ -129,3 +134,21 @@ def test_replay_of_the_references_published_run_matches_its_lammps_log():
     assert np.abs(ours[:, col["Volume"]] / ref[:, col["Volume"]] - 1.0).max() < 1e-6
     for c in ("Press", "Pxx", "Pyy", "Pzz"):
         assert np.abs(ours[:, col[c]] - ref[:, col[c]]).max() < 5.0, c         # bar; their virial is mixed precision
+
+
+def test_cg_minimiser_relaxes_a_perturbed_crystal(fe_pot_file):
+    """DomainMD.minimize on a thermally displaced cell: monotone in energy, stops on the force tolerance near the
+    perfect-lattice energy of the same box."""
+    pair, md = make_md(fe_pot_file, 4)                       # the perfect lattice of the same box (own handle)
+    md.compute(eflag=True)
+    e_perfect = float(md.engvir[0])
+    pair2, _ = make_md(fe_pot_file, 4)
+    x, box = L.bcc(4, 4, 4)
+    md_p = DomainMD(pair2, L.perturb(x, 0.08, 3), box, mass=MASS, dt=DT)
+    md_p.reneighbor()
+    st = md_p.minimize(0.0, 1.0e-6, 400, 2000)
+    assert st["stopping_criterion"] == "force tolerance" and st["fnorm_final"] < 1e-6 < st["fnorm_initial"]
+    assert st["energy_final"] < st["energy_initial"]
+    assert abs(st["energy_final"] - e_perfect) < 1e-7
+    pair.clear()
+    pair2.clear()
