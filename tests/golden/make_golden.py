@@ -216,6 +216,9 @@ def dump_fe_st_log():
     out["min_fnorm_initial_final_new"] = np.array([39.623051, 19.978295])                        # :118
     out["min_fmax_initial_final_new"] = np.array([0.93490135, 0.52800152])                       # :119
     out["min_alpha_maxmove_new"] = np.array([0.10696316, 0.056476709])                           # :120
+    # the input deck itself (1 kB of LAMMPS commands; run verbatim by meng_zhang_b200.deck in the GPU tests)
+    with open(os.path.join(OUT, "in.st_test"), "wb") as fp:
+        fp.write(z.read("performance comparsion/in.st_test"))
     np.savez_compressed(os.path.join(OUT, "fe_st_log.npz"), **out)
     print("fe_st_log:", out["thermo_new"][0], out["thermo_new"][-1][:6])
 

@@ -152,3 +152,36 @@ def test_cg_minimiser_relaxes_a_perturbed_crystal(fe_pot_file):
     assert abs(st["energy_final"] - e_perfect) < 1e-7
     pair.clear()
     pair2.clear()
+
+
+def test_the_references_input_deck_runs_verbatim(tmp_path, fe_pot_file):
+    """meng_zhang_b200.deck takes the reference's own LAMMPS deck (in.st_test) as it is - data file, potential file and
+    deck in one directory, like a LAMMPS run - and its thermo output follows the reference's LAMMPS log."""
+    import io
+    import shutil
+    from meng_zhang_b200.deck import Deck
+    from meng_zhang_b200.structures import write_lammps_data
+    z = np.load(f"{util.GOLDEN}/fe_st.npz")
+    log = np.load(f"{util.GOLDEN}/fe_st_log.npz")
+    write_lammps_data(str(tmp_path / "fe_st.dat"), z["x"], z["box"][:, 1], np.ones(len(z["x"]), dtype=np.int32), ntypes=1)
+    shutil.copy(fe_pot_file, tmp_path / "fe_annp_potential_2.ann")
+    deck = open(f"{util.GOLDEN}/in.st_test", newline="").read()
+    assert "run\t\t\t1000" in deck
+    deck = deck.replace("run\t\t\t1000", "run\t\t\t60")           # the only edit: 60 of the 1000 steps
+    with open(tmp_path / "in.st_test", "w", newline="") as fp:
+        fp.write(deck)
+    buf = io.StringIO()
+    d = Deck(out=buf)
+    d.run_file(str(tmp_path / "in.st_test"))
+    out = buf.getvalue()
+    assert "Stopping criterion = energy tolerance" in out and "Iterations, force evaluations = 1 2" in out
+    assert "Step" in out and "Loop time of" in out
+    cols = ["step", "temp", "pe", "ke", "lx", "ly", "lz", "press", "vol", "pxx", "pyy", "pzz"]      # the deck's thermo_style custom
+    assert d.thermo_cols == cols and len(d.rows) == 61
+    ref = log["thermo_new"][:61]
+    ours = np.array([[r[c] for c in cols] for r in d.rows])
+    assert np.array_equal(ours[:, 0], ref[:, 0])
+    assert np.abs(ours[:, 1] / ref[:, 1] - 1.0).max() < 5e-6                  # Temp
+    assert np.abs(ours[:, 5] - ref[:, 5]).max() < 2e-5                        # Ly
+    assert np.abs(ours[:, 7] - ref[:, 7]).max() < 5.0                         # Press (bar)
+    d.pair.clear()
