@@ -146,8 +146,9 @@ class Deck:
     def cmd_package(self, a): pass            # `package gpu N neigh no`: one rank per GPU here, nothing to configure
 
     def cmd_newton(self, a):
-        if a[0] != "on":
-            raise DeckError("Pair style annp/gpu requires newton pair on")
+        if a[0] not in ("on", "off"):
+            raise DeckError("Illegal newton command")
+        self.newton = a[0]                      # checked against the pair style in pair_coeff
 
     def cmd_units(self, a):
         if a[0] != "metal":
@@ -203,6 +204,9 @@ class Deck:
         from .pair import PairANNPGPU
         from .pair_anna import PairANNAADPGPU
         cls = PairANNPGPU if self.pair_style == "annp" else PairANNAADPGPU
+        if getattr(self, "newton", "on") == "off" and self.pair_style == "annp":
+            raise DeckError("Pair style annp/gpu requires newton pair on")        # fe_v2/src/pair_annp_gpu.cpp:139-140
+        # anna_adp: the reference's GPU decks say `newton off`, its CPU decks `newton on`; the forces are the same
         self.pair = cls(ntypes=self.ntypes, device=-1 if self.device_index is None else self.device_index, skin=self.skin)
         self.pair.settings([])
         args = list(a)

@@ -6,8 +6,8 @@
    Differences, all on purpose:
      * anna_adp_gpu_init / _compute / _compute_force / _clear / _bytes become anna_b200_init and the shared
        annp_b200_* entry points of include/annp_b200.h
-     * newton pair ON and no forward communication of rho / mu / lambda / d2 / q2: the numbers follow the reference
-       CPU style, which centres everything on the local atom (see the header)
+     * no forward communication of rho / mu / lambda / d2 / q2: the numbers follow the reference CPU style, which
+       centres everything on the local atom; `newton on` and `newton off` decks both work (see the header)
      * forces / energies are ADDED to LAMMPS' arrays; no `fix gpu` / `package gpu`; no CPU fallback
 ------------------------------------------------------------------------- */
 
@@ -40,6 +40,7 @@ PairANNAADPB200::PairANNAADPB200(LAMMPS *lmp) :
   respa_enable = 0;
   suffix_flag |= Suffix::GPU;
   comm_forward = 0;      // the CPU base class reserves one slot it never uses; nothing is forwarded here
+  comm_reverse = 3;      // ghost forces, only used under `newton off`
 }
 
 /* ---------------------------------------------------------------------- */
@@ -105,7 +106,14 @@ void PairANNAADPB200::compute(int eflag, int vflag)
   if (rc) error->one(FLERR, std::string("anna_adp/gpu: ") + annp_b200_last_error(handle));
 
   double *f0 = f[0];
-  for (int i = 0; i < 3 * nall; i++) f0[i] += fbuf[i];
+  if (force->newton_pair) {
+    // local and ghost rows: LAMMPS' reverse_comm carries the ghost part home
+    for (int i = 0; i < 3 * nall; i++) f0[i] += fbuf[i];
+  } else {
+    // `newton off`: LAMMPS will not reverse-communicate forces, so the style does it for its own ghost rows
+    comm->reverse_comm(this);
+    for (int i = 0; i < 3 * nlocal; i++) f0[i] += fbuf[i];
+  }
   if (eflag_global) eng_vdwl += eng;
   if (eflag_atom) for (int i = 0; i < nall; i++) eatom[i] += ebuf[i];
   if (want_pair_virial) for (int k = 0; k < 6; k++) virial[k] += vir[k];
@@ -116,13 +124,38 @@ void PairANNAADPB200::compute(int eflag, int vflag)
 }
 
 /* ----------------------------------------------------------------------
+   ghost forces -> owners under `newton off` (Comm::reverse_comm(Pair *))
+------------------------------------------------------------------------- */
+
+int PairANNAADPB200::pack_reverse_comm(int n, int first, double *buf)
+{
+  int m = 0;
+  for (int i = first; i < first + n; i++) {
+    buf[m++] = fbuf[3 * (size_t) i];
+    buf[m++] = fbuf[3 * (size_t) i + 1];
+    buf[m++] = fbuf[3 * (size_t) i + 2];
+  }
+  return m;
+}
+
+void PairANNAADPB200::unpack_reverse_comm(int n, int *list, double *buf)
+{
+  int m = 0;
+  for (int i = 0; i < n; i++) {
+    const int j = list[i];
+    fbuf[3 * (size_t) j] += buf[m++];
+    fbuf[3 * (size_t) j + 1] += buf[m++];
+    fbuf[3 * (size_t) j + 2] += buf[m++];
+  }
+}
+
+/* ----------------------------------------------------------------------
    init specific to this pair style   (reference: pair_anna_adp_gpu.cpp:162-260)
 ------------------------------------------------------------------------- */
 
 void PairANNAADPB200::init_style()
 {
   if (atom->tag_enable == 0) error->all(FLERR, "Pair style anna_adp/gpu requires atom IDs");
-  if (force->newton_pair == 0) error->all(FLERR, "Pair style anna_adp/gpu (B200) requires newton pair on");
 
   const ANNAPARA &p = params[0];
   const int ntl = p.ntl, nnod = p.nnod, nsf = p.nsf, nout = p.nout, nelements = p.nelements, ntypes = atom->ntypes;

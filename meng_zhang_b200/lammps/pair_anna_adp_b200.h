@@ -8,9 +8,11 @@
        pair_style  anna_adp/gpu
        pair_coeff  * * fe_adp_potential_2310.anna Fe
 
-   but run with `newton on` (the default): the numbers follow the reference CPU style (pair_anna_adp.cpp:73-286),
-   everything is centred on the local atom and LAMMPS' reverse communication carries ghost forces home, so the 12
-   forward communications per step of the reference GPU style (pair_anna_adp_gpu.cpp:135-153) disappear.
+   The numbers follow the reference CPU style (pair_anna_adp.cpp:73-286): everything is centred on the local atom, so
+   the 12 forward communications per step of the reference GPU style (pair_anna_adp_gpu.cpp:135-153) disappear and
+   only the forces on ghost atoms have to go home.  Both settings of `newton` work: with `newton on` LAMMPS' own reverse
+   communication carries them; with `newton off` - what the reference's GPU decks say (bcc_fe/README.md:39-40) - the style
+   reverse-communicates its ghost forces itself (comm->reverse_comm(this), three doubles per ghost).
 ------------------------------------------------------------------------- */
 
 #ifdef PAIR_CLASS
@@ -35,6 +37,8 @@ class PairANNAADPB200 : public PairANNA_ADP {
   void compute(int, int) override;
   void init_style() override;
   double memory_usage() override;
+  int pack_reverse_comm(int, int, double *) override;
+  void unpack_reverse_comm(int, int *, double *) override;
 
  protected:
   annp_b200_handle_s *handle;

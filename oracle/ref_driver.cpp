@@ -70,6 +70,15 @@ void forward_hook(Pair *p) {
   p->pack_forward_comm(g_in->nghost, lst.data(), buf.data(), 0, pbc);
   p->unpack_forward_comm(g_in->nghost, g_in->nlocal, buf.data());
 }
+// reverse_comm emulation (Comm::reverse_comm(Pair *)): ghost -> owner, summed
+void reverse_hook(Pair *p) {
+  int n = p->comm_reverse;
+  if (n <= 0 || g_in->nghost == 0) return;
+  std::vector<double> buf((size_t) n * g_in->nghost);
+  std::vector<int> lst(g_in->ghost_owner);
+  p->pack_reverse_comm(g_in->nghost, g_in->nlocal, buf.data());
+  p->unpack_reverse_comm(g_in->nghost, lst.data(), buf.data());
+}
 }    // namespace
 
 int main(int argc, char **argv) {
@@ -86,9 +95,11 @@ int main(int argc, char **argv) {
   lmp.memory = &memory; lmp.error = &error; lmp.atom = &atom; lmp.force = &force; lmp.comm = &comm;
   lmp.neighbor = &neighbor; lmp.update = &update; lmp.domain = &domain; lmp.screen = nullptr;
   comm.forward_hook = forward_hook;
+  comm.reverse_hook = reverse_hook;
 #ifdef NEWTON_PAIR
   force.newton_pair = NEWTON_PAIR;
 #endif
+  if (const char *nw = getenv("ANNP_DRIVER_NEWTON")) force.newton_pair = force.newton = atoi(nw);    // `newton on|off` of the deck
 
   atom.nlocal = in.nlocal; atom.nghost = in.nghost; atom.ntypes = in.ntypes; atom.nmax = nall;
   std::vector<double *> xrow(nall), frow(nall);

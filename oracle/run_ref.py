@@ -59,7 +59,7 @@ def read_output(path):
             "seconds": secs, "ncalls": ncalls}
 
 
-def run_reference(kind, cfg, potential_file, elements, eflag=3, vflag=2, ncalls=1, timeout=3600):
+def run_reference(kind, cfg, potential_file, elements, eflag=3, vflag=2, ncalls=1, timeout=3600, newton=None):
     """One `Pair::compute(eflag, vflag)` of the reference style `kind` on cfg.
 
     Returns eng_vdwl, virial[6], f[nall,3] (ghost forces NOT folded), eatom, vatom, seconds."""
@@ -69,7 +69,10 @@ def run_reference(kind, cfg, potential_file, elements, eflag=3, vflag=2, ncalls=
         fin, fout = os.path.join(td, "in.bin"), os.path.join(td, "out.bin")
         write_input(fin, cfg, eflag, vflag, ncalls)
         cmd = [BIN[kind], fin, fout, potential_file] + list(elements)
-        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        env = dict(os.environ)
+        if newton is not None:
+            env["ANNP_DRIVER_NEWTON"] = str(int(newton))      # the deck's `newton on|off`
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
         if p.returncode != 0:
             raise RuntimeError(f"reference driver failed ({p.returncode}): {p.stderr[-2000:]}")
         out = read_output(fout)

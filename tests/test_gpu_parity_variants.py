@@ -185,3 +185,18 @@ def test_ni_device_md_uses_the_descriptor_cutoff_for_its_list(ni_pot_file):
     assert abs(pair.eng_vdwl - out["tight"][1]) < 1e-10
     assert np.abs(fh - out["tight"][0]).max() < 5e-2
     pair.clear()
+
+
+@pytest.mark.parametrize("name", ["bcc4_perturbed", "bcc334_hot"])
+def test_anna_plugin_accepts_newton_off_decks(name, anna_pot_file):
+    """The reference's anna_adp/gpu decks say `newton off` (bcc_fe/README.md:39-40).  PairANNAADPB200 then returns its
+    ghost forces itself (comm->reverse_comm(this)): the local rows equal the reference CPU style's folded forces."""
+    from oracle import run_ref
+    if not run_ref.available("plugin_anna_adp_b200"):
+        pytest.skip("plugin_anna_adp_b200 not built")
+    cfg, elems, ref = util.load_case(name, "anna_adp")
+    out = run_ref.run_reference("plugin_anna_adp_b200", cfg, anna_pot_file, elems, eflag=3, vflag=1, newton=0)
+    assert np.abs(out["f"][: cfg.nlocal] - cfg.fold(ref["f"])).max() <= 1e-9
+    assert np.all(out["f"][cfg.nlocal:] == 0.0)                   # nothing is left on ghosts for LAMMPS to carry
+    assert abs(out["eng_vdwl"] - ref["eng_vdwl"]) <= 1e-12 * abs(ref["eng_vdwl"]) + 1e-9
+    assert np.abs(out["virial"] - ref["virial_pair"]).max() <= 1e-8
