@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libannp_b200.so")
+# ANNP_B200_LIB selects another build of the same library (kernel experiments); there is still no non-CUDA path behind it
+LIB_PATH = os.environ.get("ANNP_B200_LIB") or os.path.join(HERE, "lib", "libannp_b200.so")
 
 MAX_SF, MAX_NOD, MAX_LAYERS, MAX_ELEMENTS, MAX_NEIGH = 64, 32, 6, 4, 384
 ABI_VERSION = 2

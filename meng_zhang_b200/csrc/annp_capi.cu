@@ -101,7 +101,7 @@ struct annp_b200_handle_s {
   int num_sms = 0;
   cudaStream_t stream = nullptr;      // host-mode stream
   DevParams hp;                       // host copy (weights/bias pointers are device pointers)
-  DevBuf d_params, d_weights, d_bias, d_cheb2mono;
+  DevBuf d_params, d_weights, d_bias, d_cheb2mono, d_blk2cheb;
   // neighbour list
   bool have_list = false;
   int inum = 0, nall_list = 0, max_row = 0;
@@ -417,6 +417,32 @@ static int upload_params(annp_b200_handle h, const double *weights, const double
     if ((e = h->d_cheb2mono.reserve(sizeof(double) * Md.size(), 1.0)) != cudaSuccess) return bail(e, "cudaMalloc cheb2mono");
     if ((e = cudaMemcpy(h->d_cheb2mono.p, Md.data(), sizeof(double) * Md.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload cheb2mono");
     hp.cheb2mono = h->d_cheb2mono.as<double>();
+    // Forward pass basis psi_{4b+i}(z) = T_{4b}(z) z^i (annp_force.cu, stage 2): blk2cheb[j*nt+n] = X[j][n] with
+    // T_n((z+1)/2) = sum_j X[j][n] psi_j(z).  psi_j has degree exactly j, so the monomial matrix of the basis is upper
+    // triangular with power-of-two diagonal: back substitution in long double.
+    std::vector<long double> Tz((size_t) nt * nt, 0.0L), Bm((size_t) nt * nt, 0.0L), X((size_t) nt * nt, 0.0L);   // Tz[n][k]: coeff of z^k in T_n(z)
+    for (int n = 0; n < nt; n++) {
+      if (n == 0) Tz[0] = 1.0L;
+      else if (n == 1) Tz[(size_t) nt + 1] = 1.0L;
+      else
+        for (int k = 0; k < nt; k++)
+          Tz[(size_t) n * nt + k] = (k > 0 ? 2.0L * Tz[(size_t) (n - 1) * nt + k - 1] : 0.0L) - Tz[(size_t) (n - 2) * nt + k];
+    }
+    for (int j = 0; j < nt; j++) {          // Bm[k][j]: coefficient of z^k in psi_j
+      const int b4 = (j / 4) * 4, i = j % 4;
+      for (int k = 0; k + i < nt && k <= b4; k++) Bm[(size_t) (k + i) * nt + j] = Tz[(size_t) b4 * nt + k];
+    }
+    for (int n = 0; n < nt; n++)
+      for (int j = nt - 1; j >= 0; j--) {
+        long double acc = M[(size_t) j * nt + n];
+        for (int q = j + 1; q < nt; q++) acc -= Bm[(size_t) j * nt + q] * X[(size_t) q * nt + n];
+        X[(size_t) j * nt + n] = acc / Bm[(size_t) j * nt + j];
+      }
+    std::vector<double> Xd((size_t) nt * nt);
+    for (size_t q = 0; q < Xd.size(); q++) Xd[q] = (double) X[q];
+    if ((e = h->d_blk2cheb.reserve(sizeof(double) * Xd.size(), 1.0)) != cudaSuccess) return bail(e, "cudaMalloc blk2cheb");
+    if ((e = cudaMemcpy(h->d_blk2cheb.p, Xd.data(), sizeof(double) * Xd.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload blk2cheb");
+    hp.blk2cheb = h->d_blk2cheb.as<double>();
   }
   if ((e = cudaMemcpy(h->d_params.p, &hp, sizeof(DevParams), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload params");
   return ANNP_B200_OK;
@@ -494,7 +520,7 @@ int anna_b200_init(const anna_b200_params *p, int device, annp_b200_handle *out,
   hp.e_base = p->e_base;
   for (int k = 0; k < 17; k++) hp.gparams[k] = p->gparams[k];
   for (int n = 0; n < p->nsf; n++) { hp.sf_scale[n] = 1.0; hp.sf_avg[n] = 0.0; }   // raw descriptor (pair_anna_adp.cpp:124-166)
-  rc = upload_params(h, p->weights, p->bias, false, err, errlen);
+  rc = upload_params(h, p->weights, p->bias, true, err, errlen);   // the forward pass needs the block-basis conversion matrix
   if (rc) { annp_b200_clear(h); return rc; }
   *out = h;
   return ANNP_B200_OK;
@@ -504,7 +530,7 @@ void annp_b200_clear(annp_b200_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  DevBuf *bufs[] = {&h->d_cheb2mono, &h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
+  DevBuf *bufs[] = {&h->d_cheb2mono, &h->d_blk2cheb, &h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
                     &h->d_centre_of, &h->d_scratch_cnt, &h->d_scratch_tmp, &h->d_tile_sum, &h->d_cell_of, &h->d_cell_cnt,
                     &h->d_cell_off, &h->d_cell_atoms, &h->d_row_cnt, &h->d_small, &h->d_xq, &h->d_fpair, &h->d_fself, &h->d_vir_c,
                     &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,
@@ -520,7 +546,7 @@ void annp_b200_clear(annp_b200_handle h) {
 
 double annp_b200_bytes(annp_b200_handle h) {
   if (!h) return 0.0;
-  const DevBuf *bufs[] = {&h->d_cheb2mono, &h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
+  const DevBuf *bufs[] = {&h->d_cheb2mono, &h->d_blk2cheb, &h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
                           &h->d_centre_of, &h->d_scratch_cnt, &h->d_scratch_tmp, &h->d_tile_sum, &h->d_cell_of, &h->d_cell_cnt,
                           &h->d_cell_off, &h->d_cell_atoms, &h->d_row_cnt, &h->d_small, &h->d_xq, &h->d_fpair, &h->d_fself, &h->d_vir_c,
                           &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,

@@ -26,6 +26,8 @@ struct DevParams {
   const double *bias;
   // [ntsf][ntsf] row-major: monomial coefficient a_k (in z = cos theta) of T_n((z+1)/2) is cheb2mono[k*ntsf+n]
   const double *cheb2mono;
+  // [ntsf][ntsf] row-major: T_n((z+1)/2) = sum_j blk2cheb[j*ntsf+n] psi_j(z), psi_{4b+i}(z) = T_{4b}(z) z^i (forward-pass basis)
+  const double *blk2cheb;
   // ANNP_B200_VARIANT_NI: Behler-Parrinello coefficients (ni/src/pair_annp.cpp:686-767)
   int variant;
   double rad_eta[ANNP_B200_MAX_SF], rad_rc;                    // radial: eta_m, common Rc (Bohr)

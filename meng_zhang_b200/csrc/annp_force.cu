@@ -96,6 +96,26 @@ __device__ __forceinline__ Unit make_unit(const Sched &sc, int pass, int lane) {
   return u;
 }
 
+// One triplet of the forward angular pass: S[4b+i] += w T_{4b}(z) z^i  (see stage 2 of the kernel).
+template <int NTSF>
+__device__ __forceinline__ void angular_accumulate(double (&S)[NTSF], const double z, const double w) {
+  const double z2 = z * z, z3 = z2 * z;
+  const double t4 = fma(8.0, fma(z2, z2, -z2), 1.0);     // T_4(z) = 8 z^4 - 8 z^2 + 1
+  const double t4x2 = t4 + t4;
+  double pm = w, p = w;
+#pragma unroll
+  for (int b = 0; b < NTSF; b += 4) {
+    S[b] += p;
+    if (b + 1 < NTSF) S[b + 1] = fma(p, z, S[b + 1]);
+    if (b + 2 < NTSF) S[b + 2] = fma(p, z2, S[b + 2]);
+    if (b + 3 < NTSF) S[b + 3] = fma(p, z3, S[b + 3]);
+    if (b + 4 < NTSF) {
+      const double pn = (b == 0) ? t4 * w : fma(t4x2, p, -pm);
+      pm = p; p = pn;
+    }
+  }
+}
+
 // one out-of-line copy of pow(): inlined five times it is most of the ANNA instantiation's code and the kernel
 // stalls on instruction fetch (ncu r1b: stall_no_instruction 2.5 per issue)
 __device__ __noinline__ double anna_pow(double x, double y) { return pow(x, y); }
@@ -236,6 +256,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
   const double *__restrict__ sW = P.weights;
   const double *__restrict__ sBias = P.bias;
   const double *__restrict__ gC2M = P.cheb2mono;     // [NTSF][NTSF] Chebyshev -> monomial(z) matrix (L1/L2 resident)
+  const double *__restrict__ gB2C = P.blk2cheb;      // [NTSF][NTSF] forward block basis -> Chebyshev
   (void) wtot; (void) btot;
   for (int t = threadIdx.x; t < nsf; t += blockDim.x) { sScale[t] = P.sf_scale[t]; sAvg[t] = P.sf_avg[t]; }
 
@@ -380,37 +401,13 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         const double2 Akn = sA[kpn], Bkn = sB[kpn];
         const double f1 = (t < un.c1) ? B1.y : 0.0;
         const double f2 = (t >= un.t2lo && t < un.c2) ? B2.y : 0.0;
-        // Z_n = w T_n(y) obeys the same recurrence as T_n, so the 19 sums take one DFMA (recurrence) and one
-        // DADD (accumulate) per order: with the operand-reuse cache that is 4 register reads per order,
-        // which is what the FP64 pipe can issue; a 3-register DFMA per accumulate would cost 5.
-        // The two triplets of the step run one after the other (both add into S[]), so consecutive
-        // instructions share operands.
-        {
-          const double y2 = fma(A1.x, Ak.x, fma(A1.y, Ak.y, fma(B1.x, Bk.x, 1.0)));   // cos(theta) + 1 = 2y (pair_annp.cpp:671)
-          double z0 = f1 * Bk.y;
-          double z1 = (0.5 * y2) * z0;
-          S[0] += z0;
-          if (NTSF > 1) S[1] += z1;
-#pragma unroll
-          for (int n = 2; n < NTSF; n++) {
-            const double zn = fma(y2, z1, -z0);
-            S[n] += zn;
-            z0 = z1; z1 = zn;
-          }
-        }
-        {
-          const double y2 = fma(A2.x, Ak.x, fma(A2.y, Ak.y, fma(B2.x, Bk.x, 1.0)));
-          double z0 = f2 * Bk.y;
-          double z1 = (0.5 * y2) * z0;
-          S[0] += z0;
-          if (NTSF > 1) S[1] += z1;
-#pragma unroll
-          for (int n = 2; n < NTSF; n++) {
-            const double zn = fma(y2, z1, -z0);
-            S[n] += zn;
-            z0 = z1; z1 = zn;
-          }
-        }
+        // Block basis psi_{4b+i}(z) = T_{4b}(z) z^i in z = cos(theta): P_b = w T_{4b}(z) advances by the Chebyshev
+        // recurrence in T_4(z) (one DFMA per FOUR orders) and every order is ONE accumulate, S[4b+i] += P_b z^i
+        // (28 FP64 instructions per triplet for 19 orders; the order-by-order recurrence Z_n = 2y Z_{n-1} - Z_{n-2}
+        // needs 38).  The sums are converted to the reference's T_n((z+1)/2) once per atom (blk2cheb); the basis is as
+        // well conditioned as T_n itself (conversion rows sum to <= 25; parity stays at 1e-14 in G).
+        angular_accumulate<NTSF>(S, fma(A1.x, Ak.x, fma(A1.y, Ak.y, B1.x * Bk.x)), f1 * Bk.y);   // pair_annp.cpp:671-678
+        angular_accumulate<NTSF>(S, fma(A2.x, Ak.x, fma(A2.y, Ak.y, B2.x * Bk.x)), f2 * Bk.y);
         Ak = Akn; Bk = Bkn;
       }
     }
@@ -421,9 +418,12 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       if (lane == 0) sG[m] = sScale[m] * v - sScale[m] * sAvg[m];
     }
 #pragma unroll
-    for (int n = 0; n < NTSF; n++) {
-      const double v = warp_sum(S[n]);
-      if (lane == 0) sG[NPSF + n] = sScale[NPSF + n] * v - sScale[NPSF + n] * sAvg[NPSF + n];
+    for (int n = 0; n < NTSF; n++) S[n] = warp_sum(S[n]);      // every lane holds the totals
+    if (lane < NTSF) {                                          // block basis -> T_n((z+1)/2), lane n
+      double v = 0.0;
+#pragma unroll
+      for (int j = 0; j < NTSF; j++) v = fma(__ldg(gB2C + j * NTSF + lane), S[j], v);
+      sG[NPSF + lane] = sScale[NPSF + lane] * v - sScale[NPSF + lane] * sAvg[NPSF + lane];
     }
     __syncwarp();
 
