@@ -10,8 +10,8 @@
 //                                                       (reference: pair_annp.cpp:741-804)
 //   4. walks the pairs a second time, evaluating  A(y) = sum_n c_n T_n(y) and A'(y)  by Horner's rule in
 //      z = cos(theta) (2 FMA per order; c is converted to monomial coefficients once per atom) and
-//      accumulating, per neighbour, the five moments
-//          V = sum_k P u_k,  S = sum_k P cos(theta),  Aa = sum_k A fc_k     (P = A'/2 fc_j fc_k)
+//      accumulating, per neighbour, the four moments
+//          V = sum_k P u_k,  Aa = sum_k A fc_k     (P = A'/2 fc_j fc_k;  S = sum_k P cos(theta) = u_j . V)
 //      so dG/dx is never materialised and no floating-point atomics are used
 //   5. turns the moments into the force on every neighbour, F_j = -e_scale dOut/dx_j
 //      (reference: pair_annp.cpp:191-200), writes it at the neighbour's LIST position (a later
@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
   double2 *sB = sA + C;                               // uz, fc
   double2 *sC = sB + C;                               // dfc, r
   double2 *accA = sC + C;                             // Vx, Vy
-  double2 *accB = accA + C;                           // Vz, S
-  double *accC = reinterpret_cast<double *>(accB + C);   // Aa
+  double2 *accB = accA + C;                           // Vz, Aa
+  double *accC = reinterpret_cast<double *>(accB + C);   // scratch of the ANNA-ADP tail
   double2 *coefT = reinterpret_cast<double2 *>(accC + C);   // angular polynomial: NTSF monomial coefficients a_k (as doubles)
   double2 *coefR = coefT + NTSF;                      // radial  (d_m, e_m)
   double *sG = reinterpret_cast<double *>(coefR + NPSF);
@@ -299,62 +299,78 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     const int L = (int) (a.row_off[ii + 1] - p0);
 
     // ------------------------------------------------------------------ 1. filter + radial sums
+    // 1a (light, latency bound): walk the list row four 32-entry chunks at a time with all loads of the four chunks in
+    // flight together, keep the in-cutoff entries (ballot compaction, list order) and park (dx, dy, dz, r^2, 1/Rc) in
+    // the neighbour's shared-memory slot.
+    int N = 0;
+    for (int base = 0; base < L; base += 128) {
+      int jn[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = base + 32 * u + lane;
+        jn[u] = (q < L) ? (a.nbr[p0 + q] & ANNP_NEIGHMASK) : -1;
+      }
+      double4 xn[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) xn[u] = (jn[u] >= 0) ? a.xq[jn[u]] : make_double4(0.0, 0.0, 0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int q = base + 32 * u + lane;
+        const bool valid = jn[u] >= 0;
+        const double dx = xi.x - xn[u].x, dy = xi.y - xn[u].y, dz = xi.z - xn[u].z;
+        const double rsq = dx * dx + dy * dy + dz * dz;
+        const int tj = (int) xn[u].w;
+        const bool in = valid && !(rsq > P.cutsq[ti * nt1 + tj] || rsq < 1.0e-12);          // pair_annp.cpp:144
+        const unsigned mask = __ballot_sync(0xffffffffu, in);
+        const int slot = N + __popc(mask & ((1u << lane) - 1u));
+        if (in && slot < C) {
+          const int ps = ROWPOS(slot);
+          sA[ps] = make_double2(dx, dy);
+          sB[ps] = make_double2(dz, rsq);
+          sC[ps] = make_double2(P.rcinv[ti * nt1 + tj], 0.0);
+          spos[slot] = q;
+        } else if (valid) {
+          a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+          if (a.vpair) {
+            double *vp = a.vpair + (size_t) (p0 + q) * 6;
+#pragma unroll
+            for (int k = 0; k < 6; k++) vp[k] = 0.0;
+          }
+        }
+        N += __popc(mask);
+      }
+    }
+    __syncwarp();
+    // 1b (FP64): one lane per KEPT neighbour: unit vector, cutoff function, radial Chebyshev sums
     double gr[NPSF];
 #pragma unroll
     for (int m = 0; m < NPSF; m++) gr[m] = 0.0;
-    int N = 0;
-    for (int base = 0; base < L; base += 32) {
-      const int q = base + lane;
-      const bool valid = q < L;
-      bool in = false;
-      double dx = 0, dy = 0, dz = 0, rsq = 0, rci = 0;
-      if (valid) {
-        const int j = a.nbr[p0 + q] & ANNP_NEIGHMASK;
-        const double4 xj = a.xq[j];
-        dx = xi.x - xj.x; dy = xi.y - xj.y; dz = xi.z - xj.z;
-        rsq = dx * dx + dy * dy + dz * dz;
-        const int tj = (int) xj.w;
-        const double csq = P.cutsq[ti * nt1 + tj];
-        rci = P.rcinv[ti * nt1 + tj];
-        in = !(rsq > csq || rsq < 1.0e-12);          // pair_annp.cpp:144
-      }
-      const unsigned mask = __ballot_sync(0xffffffffu, in);
-      const int slot = N + __popc(mask & ((1u << lane) - 1u));
-      if (in && slot < C) {
-        const double r = sqrt(rsq);
-        const double rinv = 1.0 / r;
-        double sn, cs;
-        sincospi(r * rci, &sn, &cs);
-        const double fc = 0.5 * (cs + 1.0);          // pair_annp.cpp:590-594
-        const double dfc = -0.5 * kPi * rci * sn;
-        const int ps = ROWPOS(slot);
-        sA[ps] = make_double2(dx * rinv, dy * rinv);
-        sB[ps] = make_double2(dz * rinv, fc);
-        sC[ps] = make_double2(dfc, r);
-        accA[ps] = make_double2(0.0, 0.0);
-        accB[ps] = make_double2(0.0, 0.0);
-        accC[ps] = 0.0;
-        spos[slot] = q;
-        // radial Chebyshev sums, argument 2r/Rc - 1    (pair_annp.cpp:643-647)
-        const double xr = r * two_over_cut - 1.0, xr2 = xr + xr;
-        double t0 = 1.0, t1 = xr;
-        gr[0] += fc;
-        if (NPSF > 1) gr[1] = fma(t1, fc, gr[1]);
+    for (int sl = lane; sl < min(N, C); sl += 32) {
+      const int ps = ROWPOS(sl);
+      const double2 dA = sA[ps], dB = sB[ps];
+      const double rci = sC[ps].x;
+      const double r = sqrt(dB.y);
+      const double rinv = 1.0 / r;
+      double sn, cs;
+      sincospi(r * rci, &sn, &cs);
+      const double fc = 0.5 * (cs + 1.0);          // pair_annp.cpp:590-594
+      const double dfc = -0.5 * kPi * rci * sn;
+      sA[ps] = make_double2(dA.x * rinv, dA.y * rinv);
+      sB[ps] = make_double2(dB.x * rinv, fc);
+      sC[ps] = make_double2(dfc, r);
+      accA[ps] = make_double2(0.0, 0.0);
+      accB[ps] = make_double2(0.0, 0.0);
+      // radial Chebyshev sums, argument 2r/Rc - 1    (pair_annp.cpp:643-647)
+      const double xr = r * two_over_cut - 1.0, xr2 = xr + xr;
+      double t0 = 1.0, t1 = xr;
+      gr[0] += fc;
+      if (NPSF > 1) gr[1] = fma(t1, fc, gr[1]);
 #pragma unroll
-        for (int m = 2; m < NPSF; m++) {
-          const double t = fma(xr2, t1, -t0);
-          gr[m] = fma(t, fc, gr[m]);
-          t0 = t1; t1 = t;
-        }
-      } else if (valid) {
-        a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
-        if (a.vpair) {
-          double *vp = a.vpair + (size_t) (p0 + q) * 6;
-#pragma unroll
-          for (int k = 0; k < 6; k++) vp[k] = 0.0;
-        }
+      for (int m = 2; m < NPSF; m++) {
+        const double t = fma(xr2, t1, -t0);
+        gr[m] = fma(t, fc, gr[m]);
+        t0 = t1; t1 = t;
       }
-      N += __popc(mask);
     }
     if (lane == 0) {
       atomicMax(&a.cnt->max_neigh, N);
@@ -374,7 +390,6 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       sC[ps] = make_double2(0.0, 1.0);
       accA[ps] = make_double2(0.0, 0.0);
       accB[ps] = make_double2(0.0, 0.0);
-      accC[ps] = 0.0;
     }
     __syncwarp();
 
@@ -465,8 +480,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     for (int pass = 0; pass < sch.npass; pass++) {
       const Unit un = make_unit(sch, pass, lane);
       const double2 A1 = sA[un.m], B1 = sB[un.m], A2 = sA[Ch + un.m], B2 = sB[Ch + un.m];
-      double v1x = 0, v1y = 0, v1z = 0, s1 = 0, a1 = 0;
-      double v2x = 0, v2y = 0, v2z = 0, s2 = 0, a2 = 0;
+      double v1x = 0, v1y = 0, v1z = 0, a1 = 0;
+      double v2x = 0, v2y = 0, v2z = 0, a2 = 0;
       int e = un.elo;
       int kc = un.m + (e >> 1);
       if (kc >= M) kc -= M;
@@ -475,7 +490,6 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       for (int t = 0; t < sch.Hs; t++) {
         // this step's partner accumulators: only this lane touches them until the next __syncwarp
         double2 pa = accA[kp], pb = accB[kp];
-        double pc = accC[kp];
         // next step's partner (read-only data, prefetched across the barrier)
         e++;
         if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
@@ -487,9 +501,11 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         const double cta = fma(A1.x, Ak.x, fma(A1.y, Ak.y, B1.x * Bk.x));
         const double ctb = fma(A2.x, Ak.x, fma(A2.y, Ak.y, B2.x * Bk.x));
         // Horner with derivative in z = cos(theta):  d <- d z + b ; b <- b z + a_k   (A = b, A'(y)/2 = d)
-        double Aa_ = aK[NTSF - 1], Apa = 0.0, Ab_ = Aa_, Apb = 0.0;
+        // (first step folded by hand: d = a_top, b = a_top z + a_{top-1})
+        const double atop = aK[NTSF - 1], atop1 = aK[NTSF - 2];
+        double Apa = atop, Apb = atop, Aa_ = fma(atop, cta, atop1), Ab_ = fma(atop, ctb, atop1);
 #pragma unroll
-        for (int k = NTSF - 2; k >= 0; k--) {
+        for (int k = NTSF - 3; k >= 0; k--) {
           const double ak = aK[k];
           Apa = fma(Apa, cta, Aa_);
           Aa_ = fma(Aa_, cta, ak);
@@ -498,17 +514,16 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         }
         const double Pa = Apa * (f1 * Bk.y), Pb = Apb * (f2 * Bk.y);
         // row side (registers)
+        // (S = sum_k P cos(theta_jk) is not accumulated: it equals u_j . V_j and is formed once per neighbour in stage 5)
         v1x = fma(Pa, Ak.x, v1x); v1y = fma(Pa, Ak.y, v1y); v1z = fma(Pa, Bk.x, v1z);
-        s1 = fma(Pa, cta, s1);
         a1 = fma(Aa_, g1, a1);
         v2x = fma(Pb, Ak.x, v2x); v2y = fma(Pb, Ak.y, v2y); v2z = fma(Pb, Bk.x, v2z);
-        s2 = fma(Pb, ctb, s2);
         a2 = fma(Ab_, g2, a2);
         // partner side: ONE shared-memory read-modify-write for both triplets
-        pa.x = fma(Pa, A1.x, pa.x); pa.y = fma(Pa, A1.y, pa.y); pb.x = fma(Pa, B1.x, pb.x); pb.y = fma(Pa, cta, pb.y);
-        pa.x = fma(Pb, A2.x, pa.x); pa.y = fma(Pb, A2.y, pa.y); pb.x = fma(Pb, B2.x, pb.x); pb.y = fma(Pb, ctb, pb.y);
-        pc = fma(Aa_, f1, pc); pc = fma(Ab_, f2, pc);
-        if (un.active) { accA[kp] = pa; accB[kp] = pb; accC[kp] = pc; }
+        pa.x = fma(Pa, A1.x, pa.x); pa.y = fma(Pa, A1.y, pa.y); pb.x = fma(Pa, B1.x, pb.x);
+        pa.x = fma(Pb, A2.x, pa.x); pa.y = fma(Pb, A2.y, pa.y); pb.x = fma(Pb, B2.x, pb.x);
+        pb.y = fma(Aa_, f1, pb.y); pb.y = fma(Ab_, f2, pb.y);
+        if (un.active) { accA[kp] = pa; accB[kp] = pb; }
         __syncwarp();
         kp = kpn; Ak = Akn; Bk = Bkn;
       }
@@ -516,13 +531,11 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       for (int g = 0; g < sch.Q; g++) {
         if (un.active && un.seg == g) {
           double2 ja = accA[un.m], jb = accB[un.m];
-          ja.x += v1x; ja.y += v1y; jb.x += v1z; jb.y += s1;
+          ja.x += v1x; ja.y += v1y; jb.x += v1z; jb.y += a1;
           accA[un.m] = ja; accB[un.m] = jb;
-          accC[un.m] += a1;
           double2 oa = accA[Ch + un.m], ob = accB[Ch + un.m];
-          oa.x += v2x; oa.y += v2y; ob.x += v2z; ob.y += s2;
+          oa.x += v2x; oa.y += v2y; ob.x += v2z; ob.y += a2;
           accA[Ch + un.m] = oa; accB[Ch + un.m] = ob;
-          accC[Ch + un.m] += a2;
         }
         __syncwarp();
       }
@@ -536,7 +549,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       const int ps = ROWPOS(s);
       const double2 A = sA[ps], B = sB[ps], Cc = sC[ps];
       const double2 va = accA[ps], vb = accB[ps];
-      const double aa = accC[ps];
+      const double aa = vb.y;                                          // Aa = sum_k A fc_k
+      const double sdot = fma(va.x, A.x, fma(va.y, A.y, vb.x * B.x));  // S = sum_k P cos(theta_jk) = u_j . V_j
       const double ux = A.x, uy = A.y, uz = B.x, fc = B.y, dfc = Cc.x, r = Cc.y;
       const double rinv = 1.0 / r;
       // radial polynomial R(x) = sum c_m T_m(x) and R'(x) in the U basis
@@ -554,7 +568,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         u0 = u1; u1 = un_;
       }
       // d out / d x_j = g u_j - V / r       with dr/dx_j = -u_j, dcos/dx_j = (cos u_j - u_k)/r
-      const double g = -(Rp * two_over_cut * fc + Rv * dfc) - dfc * aa + vb.y * rinv;
+      const double g = -(Rp * two_over_cut * fc + Rv * dfc) - dfc * aa + sdot * rinv;
       const double gx = g * ux - va.x * rinv;
       const double gy = g * uy - va.y * rinv;
       const double gz = g * uz - vb.x * rinv;
