@@ -20,6 +20,7 @@ VARIANT_FE, VARIANT_NI, VARIANT_ANNA_ADP = 0, 1, 2
 MAX_GPARAMS = 32
 VARIANT_FLAG_GENERIC = 0x100
 VARIANT_FLAG_NOPAIR = 0x200
+SCATTER_GATHER, SCATTER_FIXED = 0, 1
 
 OK, ENOMEM, ENODEVICE, EINVAL, ECUDA, ESTATE, EOVERFLOW, EIO = 0, -3, -4, -20, -21, -22, -23, -24
 
@@ -140,6 +141,7 @@ PROTOTYPES = {
     "annp_b200_fp64_peak_tflops": (C.c_double, [C.c_void_p, C.c_int]),
     "annp_b200_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "annp_b200_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "annp_b200_set_scatter": (C.c_int, [C.c_void_p, C.c_int]),
     "annp_b200_debug_descriptors": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
 }
 

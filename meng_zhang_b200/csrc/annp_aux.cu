@@ -103,6 +103,19 @@ __global__ void k_gather_force(const double4 *__restrict__ fpair, const double4 
   }
 }
 
+// fixed-point scatter: f[a] = F_self(a) + accumulator(a) * 2^-ANNP_FIX_BITS   (the accumulators were filled by the force
+// kernel with 64-bit integer atomics: an exact, order-independent sum)
+__global__ void k_finish_force(const long long *__restrict__ facc, const double4 *__restrict__ fself,
+                               const int *__restrict__ centre_of, double *__restrict__ f, int nall) {
+  const double inv = 1.0 / (double) (1LL << ANNP_FIX_BITS);
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < nall; a += gridDim.x * blockDim.x) {
+    double fx = (double) facc[3 * (size_t) a] * inv, fy = (double) facc[3 * (size_t) a + 1] * inv, fz = (double) facc[3 * (size_t) a + 2] * inv;
+    const int c = centre_of[a];
+    if (c >= 0) { const double4 s = fself[c]; fx += s.x; fy += s.y; fz += s.z; }
+    f[3 * (size_t) a] = fx; f[3 * (size_t) a + 1] = fy; f[3 * (size_t) a + 2] = fz;
+  }
+}
+
 // vatom[a] = 0.5 * (sum over own row + sum over reverse entries) of the pair virials  (ev_tally_xyz split)
 __global__ void k_gather_vatom(const double *__restrict__ vpair, const int *__restrict__ centre_of,
                                const long long *__restrict__ row_off, const long long *__restrict__ rev_off,
@@ -299,6 +312,10 @@ void aux_centre_of(const int *ilist, int inum, int nall, int *centre_of, cudaStr
 void aux_gather_force(const double4 *fpair, const double4 *fself, const int *centre_of, const long long *rev_off,
                       const int *rev_pos, double *f, int nall, cudaStream_t s) {
   if (nall > 0) k_gather_force<<<grid_for((long long) nall * 32, 256, 148 * 32), 256, 0, s>>>(fpair, fself, centre_of, rev_off, rev_pos, f, nall);
+}
+
+void aux_finish_force(const long long *facc, const double4 *fself, const int *centre_of, double *f, int nall, cudaStream_t s) {
+  if (nall > 0) k_finish_force<<<grid_for(nall, 256, 148 * 8), 256, 0, s>>>(facc, fself, centre_of, f, nall);
 }
 
 void aux_gather_vatom(const double *vpair, const int *centre_of, const long long *row_off, const long long *rev_off,

@@ -24,6 +24,7 @@ void aux_build_reverse(const int *nbr, long long total, int nall, long long *rev
 void aux_centre_of(const int *ilist, int inum, int nall, int *centre_of, cudaStream_t s);
 void aux_gather_force(const double4 *fpair, const double4 *fself, const int *centre_of, const long long *rev_off,
                       const int *rev_pos, double *f, int nall, cudaStream_t s);
+void aux_finish_force(const long long *facc, const double4 *fself, const int *centre_of, double *f, int nall, cudaStream_t s);
 void aux_gather_vatom(const double *vpair, const int *centre_of, const long long *row_off, const long long *rev_off,
                       const int *rev_pos, double *vatom, int nall, cudaStream_t s);
 void aux_scatter_eatom(const double4 *fself, const int *ilist, int inum, double *eatom, cudaStream_t s);
@@ -110,7 +111,11 @@ struct annp_b200_handle_s {
   // device neighbour build scratch
   DevBuf d_cell_of, d_cell_cnt, d_cell_off, d_cell_atoms, d_row_cnt, d_small;
   // per-step
-  DevBuf d_xq, d_fpair, d_fself, d_vir_c, d_vpair, d_partial, d_counters, d_engvir, d_Gdbg, d_dEdbg;
+  DevBuf d_xq, d_fpair, d_facc, d_fself, d_vir_c, d_vpair, d_partial, d_counters, d_engvir, d_Gdbg, d_dEdbg;
+  // how neighbour forces reach f: 1 = fixed-point integer atomics into d_facc (Chebyshev ANNP, ANNA-ADP: default),
+  // 0 = per-entry pair forces (d_fpair) summed by an ordered gather over the reverse map (Ni copy; selectable for the others)
+  int scatter_fixed = 0;
+  bool have_reverse = false;
   // host-mode staging
   DevBuf d_x, d_type, d_f, d_eatom, d_vatom;
   // ghosts
@@ -160,22 +165,33 @@ int round_capacity(int n) {
 }
 
 int finish_list(annp_b200_handle h, cudaStream_t s) {
-  // reverse map + centre index for the list now in d_ilist / d_row_off / d_nbr
+  // centre index for the list now in d_ilist / d_row_off / d_nbr; the reverse map is built on first use (ensure_reverse)
   const int nall = h->nall_list;
   if (h->total >= (1LL << 31)) return fail(h, ANNP_B200_EINVAL, "neighbour list has 2^31 or more entries");
+  CK(h->d_centre_of.reserve(sizeof(int) * (size_t) std::max(nall, 1)));
+  aux_centre_of(h->d_ilist.as<int>(), h->inum, nall, h->d_centre_of.as<int>(), s);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  h->have_list = true;
+  h->have_reverse = false;
+  h->need_calibrate = true;
+  return ANNP_B200_OK;
+}
+
+// reverse map (for every atom the list positions that name it, ascending): needed by the ordered gather and by vatom
+int ensure_reverse(annp_b200_handle h, cudaStream_t s) {
+  if (h->have_reverse) return ANNP_B200_OK;
+  const int nall = h->nall_list;
   CK(h->d_rev_off.reserve(sizeof(long long) * ((size_t) nall + 1)));
   CK(h->d_rev_pos.reserve(sizeof(int) * (size_t) std::max<long long>(h->total, 1)));
   CK(h->d_scratch_cnt.reserve(sizeof(int) * (size_t) std::max(nall, 1)));
   CK(h->d_scratch_tmp.reserve(sizeof(int) * (size_t) std::max<long long>(h->total, 1)));
   CK(h->d_tile_sum.reserve(sizeof(long long) * ((size_t) nall / 1024 + 2)));
-  CK(h->d_centre_of.reserve(sizeof(int) * (size_t) std::max(nall, 1)));
   aux_build_reverse(h->d_nbr.as<int>(), h->total, nall, h->d_rev_off.as<long long>(), h->d_rev_pos.as<int>(),
                     h->d_scratch_cnt.as<int>(), h->d_scratch_tmp.as<int>(), h->d_tile_sum.as<long long>(), s);
-  aux_centre_of(h->d_ilist.as<int>(), h->inum, nall, h->d_centre_of.as<int>(), s);
-  h->launches += 9;
+  h->launches += 8;
   CK(cudaGetLastError());
-  h->have_list = true;
-  h->need_calibrate = true;
+  h->have_reverse = true;
   return ANNP_B200_OK;
 }
 
@@ -190,7 +206,10 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
   const int inum = h->inum;
 
   CK(h->d_xq.reserve(sizeof(double4) * (size_t) std::max(nall, 1)));
-  CK(h->d_fpair.reserve(sizeof(double4) * (size_t) std::max<long long>(h->total, 1)));
+  const bool fixed = h->scatter_fixed != 0;
+  if (fixed) CK(h->d_facc.reserve(sizeof(long long) * 3 * (size_t) std::max(nall, 1)));
+  else CK(h->d_fpair.reserve(sizeof(double4) * (size_t) std::max<long long>(h->total, 1)));
+  if (!fixed || want_vatom) { int rc = ensure_reverse(h, s); if (rc) return rc; }
   CK(h->d_fself.reserve(sizeof(double4) * (size_t) std::max(inum, 1)));
   CK(h->d_counters.reserve(sizeof(DevCounters)));
   CK(h->d_partial.reserve(sizeof(double) * 7 * (size_t) aux_reduce_blocks(inum)));
@@ -235,7 +254,9 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
   a.ilist = h->d_ilist.as<int>();
   a.row_off = h->d_row_off.as<long long>();
   a.nbr = h->d_nbr.as<int>();
-  a.fpair = h->d_fpair.as<double4>();
+  a.fpair = fixed ? nullptr : h->d_fpair.as<double4>();
+  a.facc = fixed ? h->d_facc.as<long long>() : nullptr;
+  if (fixed) CK(cudaMemsetAsync(h->d_facc.p, 0, sizeof(long long) * 3 * (size_t) std::max(nall, 1), s));
   a.fself = h->d_fself.as<double4>();
   a.vir_c = (want_vir || want_vatom) ? h->d_vir_c.as<double>() : nullptr;
   a.vpair = want_vatom ? h->d_vpair.as<double>() : nullptr;
@@ -254,7 +275,10 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
     if (timed) { CK(cudaEventRecord(h->ev1[h->ev_count], s)); h->ev_count++; }
     h->launches += 1;
   }
-  if (d_f) {
+  if (d_f && fixed) {
+    aux_finish_force(h->d_facc.as<long long>(), h->d_fself.as<double4>(), h->d_centre_of.as<int>(), d_f, nall, s);
+    h->launches += 1;
+  } else if (d_f) {
     aux_gather_force(h->d_fpair.as<double4>(), h->d_fself.as<double4>(), h->d_centre_of.as<int>(), h->d_rev_off.as<long long>(),
                      h->d_rev_pos.as<int>(), d_f, nall, s);
     h->launches += 1;
@@ -491,6 +515,7 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
   }
   rc = upload_params(h, p->weights, p->bias, !ni, err, errlen);
   if (rc) { annp_b200_clear(h); return rc; }
+  h->scatter_fixed = ni ? 0 : 1;
   *out = h;
   return ANNP_B200_OK;
 }
@@ -522,6 +547,7 @@ int anna_b200_init(const anna_b200_params *p, int device, annp_b200_handle *out,
   for (int n = 0; n < p->nsf; n++) { hp.sf_scale[n] = 1.0; hp.sf_avg[n] = 0.0; }   // raw descriptor (pair_anna_adp.cpp:124-166)
   rc = upload_params(h, p->weights, p->bias, true, err, errlen);   // the forward pass needs the block-basis conversion matrix
   if (rc) { annp_b200_clear(h); return rc; }
+  h->scatter_fixed = 1;
   *out = h;
   return ANNP_B200_OK;
 }
@@ -532,7 +558,7 @@ void annp_b200_clear(annp_b200_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   DevBuf *bufs[] = {&h->d_cheb2mono, &h->d_blk2cheb, &h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
                     &h->d_centre_of, &h->d_scratch_cnt, &h->d_scratch_tmp, &h->d_tile_sum, &h->d_cell_of, &h->d_cell_cnt,
-                    &h->d_cell_off, &h->d_cell_atoms, &h->d_row_cnt, &h->d_small, &h->d_xq, &h->d_fpair, &h->d_fself, &h->d_vir_c,
+                    &h->d_cell_off, &h->d_cell_atoms, &h->d_row_cnt, &h->d_small, &h->d_xq, &h->d_fpair, &h->d_facc, &h->d_fself, &h->d_vir_c,
                     &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,
                     &h->d_eatom, &h->d_vatom, &h->d_goff, &h->d_glist, &h->d_ke_partial};
   for (DevBuf *b : bufs) b->release();
@@ -548,7 +574,7 @@ double annp_b200_bytes(annp_b200_handle h) {
   if (!h) return 0.0;
   const DevBuf *bufs[] = {&h->d_cheb2mono, &h->d_blk2cheb, &h->d_params, &h->d_weights, &h->d_bias, &h->d_ilist, &h->d_row_off, &h->d_nbr, &h->d_rev_off, &h->d_rev_pos,
                           &h->d_centre_of, &h->d_scratch_cnt, &h->d_scratch_tmp, &h->d_tile_sum, &h->d_cell_of, &h->d_cell_cnt,
-                          &h->d_cell_off, &h->d_cell_atoms, &h->d_row_cnt, &h->d_small, &h->d_xq, &h->d_fpair, &h->d_fself, &h->d_vir_c,
+                          &h->d_cell_off, &h->d_cell_atoms, &h->d_row_cnt, &h->d_small, &h->d_xq, &h->d_fpair, &h->d_facc, &h->d_fself, &h->d_vir_c,
                           &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,
                           &h->d_eatom, &h->d_vatom, &h->d_goff, &h->d_glist, &h->d_ke_partial};
   double b = 0.0;
@@ -625,6 +651,10 @@ int annp_b200_compute(annp_b200_handle h, int nlocal, int nghost, const double *
     if (rc) return rc;
     rc = fetch_counters(h, s);
     if (rc) return rc;
+    if (h->last_cnt.bad_force) {
+      CK(cudaMemsetAsync(h->d_counters.p, 0, sizeof(DevCounters), s));
+      return fail(h, ANNP_B200_EOVERFLOW, "a pair force is NaN or beyond 2^18 eV/A (fixed-point force accumulation): the configuration is unphysical");
+    }
     if (!h->last_cnt.overflow) break;
     // a neighbour tile overflowed (atoms moved inside the skin): grow and redo the step
     if (h->last_cnt.max_neigh > ANNP_B200_MAX_NEIGH) return fail(h, ANNP_B200_EOVERFLOW, "an atom has more in-cutoff neighbours than ANNP_B200_MAX_NEIGH");
@@ -774,6 +804,15 @@ int annp_b200_get_stats(annp_b200_handle h, annp_b200_stats *out) {
   out->force_kernel_ms_total = h->force_ms_total;
   out->force_kernel_samples = h->force_samples;
   if (h->last_cnt.overflow) return fail(h, ANNP_B200_EOVERFLOW, "neighbour tile overflow in a device-mode step: results of that step are invalid");
+  if (h->last_cnt.bad_force) return fail(h, ANNP_B200_EOVERFLOW, "a pair force was NaN or beyond 2^18 eV/A in a device-mode step (fixed-point force accumulation)");
+  return ANNP_B200_OK;
+}
+
+int annp_b200_set_scatter(annp_b200_handle h, int mode) {
+  if (!h || (mode != ANNP_B200_SCATTER_GATHER && mode != ANNP_B200_SCATTER_FIXED)) return ANNP_B200_EINVAL;
+  if (mode == ANNP_B200_SCATTER_FIXED && h->hp.variant == ANNP_B200_VARIANT_NI)
+    return fail(h, ANNP_B200_EINVAL, "the Ni kernels write per-entry pair forces: only ANNP_B200_SCATTER_GATHER is available");
+  h->scatter_fixed = mode == ANNP_B200_SCATTER_FIXED;
   return ANNP_B200_OK;
 }
 

@@ -6,6 +6,10 @@
 
 #define ANNP_NEIGHMASK 0x1FFFFFFF
 #define ANNP_MAX_TYPES 8
+// fixed-point force accumulation: 1 unit = 2^-43 eV/A (1.1e-13); int64 holds +-1.0e6 eV/A; contributions are refused
+// (bad_force flag) from 2^18 eV/A on, so 4 billion of them could be summed before the accumulator wraps
+#define ANNP_FIX_BITS 43
+#define ANNP_FIX_LIMIT_BITS 18
 
 // Parameter block resident in global memory (one per handle); kernels stage what they need in smem.
 struct DevParams {
@@ -44,6 +48,7 @@ struct DevCounters {
   unsigned long long sum_trip;    // sum of N(N-1)/2
   int max_neigh;                  // max in-cutoff neighbours
   int overflow;                   // an atom exceeded the smem capacity
+  int bad_force;                  // a neighbour force left the fixed-point range (|F| >= 2^ANNP_FIX_LIMIT_BITS eV/A) or is NaN
 };
 
 struct ForceArgs {
@@ -52,7 +57,10 @@ struct ForceArgs {
   const int *ilist;           // [inum]
   const long long *row_off;   // [inum+1]
   const int *nbr;             // [total]
-  double4 *fpair;             // [total] force on the neighbour of every list entry (0 if outside Rc)
+  double4 *fpair;             // [total] force on the neighbour of every list entry (0 if outside Rc); ordered-gather scatter
+  long long *facc;            // [nall][3] fixed-point force accumulators (units of 2^-ANNP_FIX_BITS eV/A); when non-null the
+                              // neighbour forces are added here with 64-bit integer atomics (exact, order independent)
+                              // and fpair is not touched
   double4 *fself;             // [inum]  x,y,z = -sum_j Fj ; w = E_i
   double *vir_c;              // [inum][6] per-centre pair virial (may be null)
   double *vpair;              // [total][6] per-pair virial for vatom (may be null)
@@ -157,6 +165,19 @@ __device__ __forceinline__ void annp_mlp_forward_warp(const DevParams &P, const 
     __syncwarp();
     in = sH + l * nnod;
   }
+}
+
+// add (fx, fy, fz) to the fixed-point accumulator of atom j; false if a component is outside the representable range
+__device__ __forceinline__ bool annp_fix_add(long long *facc, int j, double fx, double fy, double fz) {
+  const double lim = (double) (1LL << ANNP_FIX_LIMIT_BITS), sc = (double) (1LL << ANNP_FIX_BITS);
+  const bool ok = fabs(fx) < lim && fabs(fy) < lim && fabs(fz) < lim;      // false for NaN as well
+  if (ok) {
+    unsigned long long *t = reinterpret_cast<unsigned long long *>(facc + 3 * (size_t) j);
+    atomicAdd(t, (unsigned long long) __double2ll_rn(fx * sc));
+    atomicAdd(t + 1, (unsigned long long) __double2ll_rn(fy * sc));
+    atomicAdd(t + 2, (unsigned long long) __double2ll_rn(fz * sc));
+  }
+  return ok;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -126,6 +126,7 @@ __device__ __noinline__ double anna_pow(double x, double y) { return pow(x, y); 
 //   positions like the ANNP forces.  One lane per neighbour, fixed butterfly sums -> deterministic.
 //   The transcendental factors of a neighbour (three powers, three exponentials) are the same in the sum pass and in
 //   the force pass: they are computed once and parked in the shared-memory slots the ANNP backward pass would use.
+template <bool FIXED>
 __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParams &P, const double *We, const double *Be,
                                               const double *sG, double *sH, const double2 *sA, const double2 *sB,
                                               double2 *sC, double2 *accA, double2 *accB, double *accC, const int *spos, int N,
@@ -213,7 +214,11 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
       fy = df1 * y * rinv + aw * (y * lyy + z * lyz + x * lxy) + my * au + y * df3;
       fz = df1 * z * rinv + aw * (y * lyz + z * lzz + x * lxz) + mz * au + z * df3;
     }
-    a.fpair[p0 + q] = make_double4(fx, fy, fz, 0.0);                  // f[j] += (fx, fy, fz), f[i] -=
+    if constexpr (FIXED) {                                            // f[j] += (fx, fy, fz), f[i] -=
+      if (!annp_fix_add(a.facc, a.nbr[p0 + q] & ANNP_NEIGHMASK, fx, fy, fz)) atomicExch(&a.cnt->bad_force, 1);
+    } else {
+      a.fpair[p0 + q] = make_double4(fx, fy, fz, 0.0);
+    }
     fix -= fx; fiy -= fy; fiz -= fz;
     if (a.vir_c || a.vpair) {                                         // ev_tally_xyz(i, j, .., -f, x_ij)
       const double w0 = -x * fx, w1 = -y * fy, w2 = -z * fz, w3 = -x * fy, w4 = -x * fz, w5 = -y * fz;
@@ -238,7 +243,7 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
 #undef ROWPOS
 }
 
-template <int NPSF, int NTSF, int MODE>
+template <int NPSF, int NTSF, int MODE, bool FIXED>
 __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -272,6 +277,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
   double2 *accA = sC + C;                             // Vx, Vy
   double2 *accB = accA + C;                           // Vz, Aa
   double *accC = reinterpret_cast<double *>(accB + C);   // scratch of the ANNA-ADP tail
+  int *sj = reinterpret_cast<int *>(accC);            // Chebyshev ANNP, fixed-point scatter: atom index of the kept neighbour
   double2 *coefT = reinterpret_cast<double2 *>(accC + C);   // angular polynomial: NTSF monomial coefficients a_k (as doubles)
   double2 *coefR = coefT + NTSF;                      // radial  (d_m, e_m)
   double *sG = reinterpret_cast<double *>(coefR + NPSF);
@@ -329,8 +335,9 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
           sB[ps] = make_double2(dz, rsq);
           sC[ps] = make_double2(P.rcinv[ti * nt1 + tj], 0.0);
           spos[slot] = q;
+          if constexpr (FIXED && MODE == 0) sj[slot] = jn[u];
         } else if (valid) {
-          a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+          if constexpr (!FIXED) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
           if (a.vpair) {
             double *vp = a.vpair + (size_t) (p0 + q) * 6;
 #pragma unroll
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     }
     if (N + (N & 1) > C) {   // capacity exceeded: flag it, emit zeros; the host re-runs with a larger tile
       if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
-      for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+      if constexpr (!FIXED) for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
       __syncwarp();
       continue;
     }
@@ -446,7 +453,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     const double *We = sW + elem * P.w_per_elem;
     const double *Be = sBias + elem * P.b_per_elem;
     if constexpr (MODE == 1) {      // ANNA-ADP: forward network + ADP energy and forces, no descriptor derivatives
-      anna_adp_tail(a, P, We, Be, sG, sH, sA, sB, sC, accA, accB, accC, spos, N, Ch, p0, ii, lane);
+      anna_adp_tail<FIXED>(a, P, We, Be, sG, sH, sA, sB, sC, accA, accB, accC, spos, N, Ch, p0, ii, lane);
       continue;
     }
 
@@ -574,7 +581,11 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       const double gz = g * uz - vb.x * rinv;
       const double Fx = mes * gx, Fy = mes * gy, Fz = mes * gz;     // pair_annp.cpp:197
       const int q = spos[s];
-      a.fpair[p0 + q] = make_double4(Fx, Fy, Fz, 0.0);
+      if constexpr (FIXED) {
+        if (!annp_fix_add(a.facc, sj[s], Fx, Fy, Fz)) atomicExch(&a.cnt->bad_force, 1);
+      } else {
+        a.fpair[p0 + q] = make_double4(Fx, Fy, Fz, 0.0);
+      }
       fix -= Fx; fiy -= Fy; fiz -= Fz;
       if (a.vir_c || a.vpair) {
         // ev_tally_xyz(i, j, ..., -Fj, xi - xj)     (pair_annp.cpp:201-209)
@@ -617,16 +628,21 @@ size_t annp_force_smem_bytes(const DevParams &hp, int capacity) {
 
 typedef void (*force_kernel_t)(const ForceArgs);
 
-static force_kernel_t pick_kernel(int npsf, int ntsf, int variant = ANNP_B200_VARIANT_FE) {
+template <bool FIXED>
+static force_kernel_t pick_kernel_t(int npsf, int ntsf, int variant) {
   if (variant == ANNP_B200_VARIANT_ANNA_ADP) {
-    if (npsf == 9 && ntsf == 19) return annp_force_kernel<9, 19, 1>;  // fe_adp_potential_2310.anna
-    if (npsf == 4 && ntsf == 6) return annp_force_kernel<4, 6, 1>;
+    if (npsf == 9 && ntsf == 19) return annp_force_kernel<9, 19, 1, FIXED>;  // fe_adp_potential_2310.anna
+    if (npsf == 4 && ntsf == 6) return annp_force_kernel<4, 6, 1, FIXED>;
     return nullptr;
   }
-  if (npsf == 9 && ntsf == 19) return annp_force_kernel<9, 19, 0>;     // fe / fe_v2 potential
-  if (npsf == 8 && ntsf == 20) return annp_force_kernel<8, 20, 0>;
-  if (npsf == 4 && ntsf == 6) return annp_force_kernel<4, 6, 0>;       // small set used by unit tests
+  if (npsf == 9 && ntsf == 19) return annp_force_kernel<9, 19, 0, FIXED>;     // fe / fe_v2 potential
+  if (npsf == 8 && ntsf == 20) return annp_force_kernel<8, 20, 0, FIXED>;
+  if (npsf == 4 && ntsf == 6) return annp_force_kernel<4, 6, 0, FIXED>;       // small set used by unit tests
   return nullptr;
+}
+// fixed: neighbour forces go to the fixed-point accumulators (args.facc) instead of the per-entry buffer (args.fpair)
+static force_kernel_t pick_kernel(int npsf, int ntsf, int variant = ANNP_B200_VARIANT_FE, bool fixed = false) {
+  return fixed ? pick_kernel_t<true>(npsf, ntsf, variant) : pick_kernel_t<false>(npsf, ntsf, variant);
 }
 
 bool annp_force_supported(int npsf, int ntsf) { return pick_kernel(npsf, ntsf) != nullptr; }
@@ -634,7 +650,7 @@ bool annp_force_supported(int npsf, int ntsf) { return pick_kernel(npsf, ntsf) !
 // Launch on `stream`. grid_blocks <= 0 picks one full wave of resident blocks.
 cudaError_t annp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream,
                               int *blocks_out) {
-  force_kernel_t k = pick_kernel(hp.npsf, hp.ntsf, hp.variant);
+  force_kernel_t k = pick_kernel(hp.npsf, hp.ntsf, hp.variant, args.facc != nullptr);
   if (!k) return cudaErrorInvalidValue;
   const size_t smem = annp_force_smem_bytes(hp, args.capacity);
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);

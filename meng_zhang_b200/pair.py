@@ -356,6 +356,10 @@ class PairANNPGPU:
         self._check(L.annp_b200_debug_descriptors(self.handle, _dp(G), _dp(dE)))
         return G, dE
 
+    def set_scatter(self, mode: int) -> None:
+        """capi.SCATTER_FIXED (default for the Chebyshev / ANNA-ADP styles) or capi.SCATTER_GATHER, see include/annp_b200.h."""
+        self._check(capi.lib().annp_b200_set_scatter(self.handle, int(mode)))
+
     def stats(self):
         st = capi.Stats()
         self._check(capi.lib().annp_b200_get_stats(self.handle, C.byref(st)))

@@ -18,13 +18,15 @@ from test_gpu_parity import build_large_config  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--cells", type=int, default=40)
 ap.add_argument("--steps", type=int, default=5)
+ap.add_argument("--scatter", default="fixed", choices=["fixed", "gather"])
 a = ap.parse_args()
 pot = util.write_fe_potential("/tmp/annp_b200_fkt_fe.ann")
 pair = PairANNPGPU(ntypes=1)
 pair.settings([])
 pair.coeff(["*", "*", pot, "Fe"])
 pair.init_style()
-out = {"lib": os.path.basename(capi.LIB_PATH)}
+pair.set_scatter(capi.SCATTER_FIXED if a.scatter == "fixed" else capi.SCATTER_GATHER)
+out = {"scatter": a.scatter, "lib": os.path.basename(capi.LIB_PATH)}
 from oracle import restatement  # noqa: E402
 x, box = L.bcc(4, 4, 4)
 cfg = L.build_config(L.perturb(x, 0.08, 99), box, 6.5)
@@ -39,8 +41,11 @@ for _ in range(2):
     pair.compute(1, 0, cfg, ago=1)
 lib = capi.lib()
 lib.annp_b200_set_timing(pair.handle, 1)
+import time  # noqa: E402
+t0 = time.perf_counter()
 for _ in range(a.steps):
     pair.compute(1, 0, cfg, ago=1)
+out["host_call_ms"] = (time.perf_counter() - t0) / a.steps * 1e3
 st = pair.stats()
 ms = st.force_kernel_ms_total / max(st.force_kernel_samples, 1)
 out.update({"atoms": cfg.nlocal, "neighbors_in_cutoff": st.avg_neigh_cut, "force_kernel_ms": ms,

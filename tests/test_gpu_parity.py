@@ -48,6 +48,29 @@ def test_golden_case(name, fe_pot_file):
     pair.clear()
 
 
+@pytest.mark.parametrize("name", ["bcc4_perturbed", "cluster_ragged"])
+def test_scatter_modes_agree(name, fe_pot_file):
+    """Fixed-point integer atomics (default) and the ordered FP64 gather give the same forces to the fixed-point
+    resolution (2^-43 eV/A per pair force), both match the reference, both are bit-reproducible."""
+    cfg, elems, ref = util.load_case(name)
+    pair = make_pair(fe_pot_file, elems)
+    f_fixed = pair.compute(3, 1 + 4, cfg, ago=0)
+    va_fixed = pair.vatom.copy()
+    assert np.array_equal(f_fixed, pair.compute(1, 0, cfg, ago=1))
+    pair.set_scatter(capi.SCATTER_GATHER)
+    f_gather = pair.compute(3, 1 + 4, cfg, ago=1)
+    va_gather = pair.vatom.copy()
+    assert np.array_equal(f_gather, pair.compute(1, 0, cfg, ago=1))
+    assert np.abs(f_fixed - f_gather).max() <= 2e-11
+    assert np.abs(f_fixed - ref["f"]).max() <= TOL_F and np.abs(f_gather - ref["f"]).max() <= TOL_F
+    assert np.array_equal(va_fixed, va_gather)
+    pair.set_scatter(capi.SCATTER_FIXED)
+    assert np.array_equal(f_fixed, pair.compute(1, 0, cfg, ago=1))
+    # the sum of all forces (ghost forces folded) vanishes to the rounding of the centre sums
+    assert np.abs(cfg.fold(f_fixed).sum(axis=0)).max() <= 1e-10
+    pair.clear()
+
+
 def test_against_live_oracle_random_configuration(fe_pot_file):
     from oracle import restatement
     x, box = L.bcc(5, 4, 3)
