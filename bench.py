@@ -6,8 +6,8 @@
 Workload (config.workload): BASELINE.json configs[4], the weak-scaling cell - 64x64x64 bcc-Fe cells
 = 524 288 atoms PER GPU (a=2.8553 A, thermally perturbed lattice, 300 K velocities, PBC, 2 A skin),
 potential fe_annp_potential_2 (28 SF, 28-10-10-1).  One step = one velocity-Verlet MD step: forward
-halo, force evaluation (pack, fused descriptor/MLP/force kernel, deterministic gather), reverse halo,
-integration.  N ranks = LAMMPS-style brick decomposition 1x1x1 / 2x1x1 / 2x2x1 / 2x2x2, one rank per
+halo, force evaluation (pack, fused descriptor/MLP/force kernel with fixed-point force scatter, conversion),
+reverse halo, integration.  N ranks = LAMMPS-style brick decomposition 1x1x1 / 2x1x1 / 2x2x1 / 2x2x2, one rank per
 GPU, halo exchange on device buffers over NCCL.
 
 value   device-resident MD (positions never leave HBM), CUDA-event timed, max over ranks
@@ -38,6 +38,7 @@ A_FE = 2.8553
 RC = 6.5
 SKIN = 2.0
 FLOP_TRIPLET, FLOP_PAIR, FLOP_MLP = 278.0, 168.0, 1560.0     # F_alg = 278 T + 168 N + 1560
+NCU_TRAFFIC_BYTES = 4.2727e9                                 # profiles/r1c_force_kernel.md (updated with every committed capture)
 PUBLISHED_ATOM_STEPS_PER_S = 152880 * 1000 / 1789.44         # BASELINE.md section 1 (the reference's own 2-GPU log)
 
 
@@ -224,7 +225,7 @@ def run_ours(args):
     e2e_value = natoms_total * args.steps / float(t_e2e)
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_baseline_reference(sample_cells=10, repeats=1)
+        cpu_base = cpu_baseline_reference(sample_cells=10, repeats=3)
     published = None
     if rank == 0 and world == 1 and not args.no_published_deck:
         published = run_published_deck(pot_file, dev)
@@ -246,14 +247,12 @@ def run_ours(args):
                        "potential": "fe_annp_potential_2 (28 SF = 9 radial + 19 angular, 28-10-10-1, Rc 6.5 A)",
                        "atoms_per_gpu": nlocal, "ghosts_per_gpu": md.nghost, "decomposition": "x".join(map(str, grid)),
                        "neighbors_in_cutoff": st.avg_neigh_cut, "list_neighbors": st0.max_neigh_list,
-                       "l2_policy": "inputs larger than L2 (neighbour list + pair-force buffers are GBs per step)"},
+                       "l2_policy": "inputs larger than L2 (every step streams the 0.49 GB neighbour list of 524288 x 234 entries; L2 is 126 MB)"},
             "roofline": {"bound": "fp64", "kernel": "annp_force_kernel<9,19>", "achieved": achieved_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at exactly this workload
-                         # (profiles/r1b_force_kernel.md: 0.535 GB read + 3.737 GB written, 32 B per list entry of
-                         # pair forces); algorithmic bytes are ~0.94 kB/atom = 0.49 GB, the rest is the deterministic
-                         # scatter buffer, 1.8 % of the measured HBM peak and hidden behind the FP64 pipe
-                         "traffic": 4.2727e9 if (cells == 64 and world == 1) else None,
+                         # (profiles/r1c_force_kernel.md); algorithmic bytes are ~0.94 kB/atom = 0.49 GB
+                         "traffic": NCU_TRAFFIC_BYTES if (cells == 64 and world == 1) else None,
                          "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / (ms_total / args.steps),
                          "flop_per_atom_step": flop_per_launch / nlocal,
                          "peak_source": "measured on this GPU by annp_b200_fp64_peak_tflops (pure DFMA loop); "
@@ -353,7 +352,7 @@ def cpu_baseline_reference(sample_cells=10, repeats=1, cores=None):
         kind = "port"
         how = f"oracle/annp_oracle.c with {cores} OpenMP threads"
     return {"value": natoms / dt, "unit": "atom-steps/s", "cores": cores, "kind": kind,
-            "sample": f"{sample_cells}^3 bcc cells = {natoms} atoms of the same lattice (one force evaluation incl. process start-up), {how}",
+            "sample": f"{sample_cells}^3 bcc cells = {natoms} atoms of the same lattice (mean of {repeats} force evaluation(s), each incl. process start-up), {how}",
             "seconds": dt}
 
 
