@@ -35,15 +35,21 @@
 // by the FP64 FMA pipe, see DESIGN.md.
 #include "annp_device.cuh"
 
-#include <type_traits>
-
-#ifndef ANNP_SPLIT_VARIANT
-#define ANNP_SPLIT_VARIANT 0
+#ifndef ANNP_KWARPS
+#define ANNP_KWARPS 4
+#endif
+#ifndef ANNP_MINBLOCKS
+#define ANNP_MINBLOCKS 4
+#endif
+#ifdef ANNP_EXP_UNROLL2
+#define ANNP_STEP_UNROLL _Pragma("unroll 2")
+#else
+#define ANNP_STEP_UNROLL _Pragma("unroll 1")
 #endif
 
 namespace {
 
-constexpr int kWarps = 4;            // warps per block; each warp is independent
+constexpr int kWarps = ANNP_KWARPS;            // warps per block; each warp is independent
 constexpr double kPi = 3.14159265358979323846;
 
 // One lane's work unit in a pass over the row pairs: row pair m, steps e = elo + t for t < nsteps.
@@ -102,17 +108,8 @@ __device__ __forceinline__ Unit make_unit(const Sched &sc, int pass, int lane) {
   return u;
 }
 
-// Warp-uniform step ranges of a pass: steps [lo, hi) are complete (both triplets valid) on every active lane, the
-// pass ends at `end` (no lane has work beyond it).
-struct StepRange { int lo, hi, end; };
-__device__ __forceinline__ StepRange make_range(const Unit &u) {
-  StepRange r;
-  r.end = __reduce_max_sync(0xffffffffu, max(u.c1, u.c2));
-  r.lo = min(r.end, (int) __reduce_max_sync(0xffffffffu, u.active ? u.t2lo : 0));
-  const int hi = __reduce_min_sync(0xffffffffu, u.active ? min(u.c1, u.c2) : 0x7fffffff);
-  r.hi = max(r.lo, min(r.end, hi));
-  return r;
-}
+// Steps a pass needs: no lane of the warp has a valid triplet at or beyond this step (warp uniform).
+__device__ __forceinline__ int pass_end(const Unit &u) { return __reduce_max_sync(0xffffffffu, max(u.c1, u.c2)); }
 
 // One triplet of the forward angular pass: S[4b+i] += w T_{4b}(z) z^i  (see stage 2 of the kernel).
 template <int NTSF>
@@ -262,7 +259,7 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
 }
 
 template <int NPSF, int NTSF, int MODE, bool FIXED>
-__global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, ANNP_MINBLOCKS) annp_force_kernel(const ForceArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const DevParams &P = *a.prm;
@@ -427,9 +424,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     for (int n = 0; n < NTSF; n++) S[n] = 0.0;
     for (int pass = 0; pass < sch.npass; pass++) {
       const Unit un = make_unit(sch, pass, lane);
-      const StepRange rg = make_range(un);
+      const int end = pass_end(un);
       double2 A1 = sA[un.m], B1 = sB[un.m], A2 = sA[Ch + un.m], B2 = sB[Ch + un.m];
-      if (!un.active) { A1 = B1 = A2 = B2 = make_double2(0.0, 0.0); }     // idle lanes: zero weight, no masks needed
       // partner position: parity half of e, index (m + e/2) mod M
       int e = un.elo;
       int kc = un.m + (e >> 1);
@@ -441,46 +437,20 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       // (28 FP64 instructions per triplet for 19 orders; the order-by-order recurrence Z_n = 2y Z_{n-1} - Z_{n-2}
       // needs 38).  The sums are converted to the reference's T_n((z+1)/2) once per atom (blk2cheb); the basis is as
       // well conditioned as T_n itself (conversion rows sum to <= 25; parity stays at 1e-14 in G).
-      auto step = [&](auto masked) {
+      auto step = [&]() {
         // next step: e + 1 flips the parity half; the index advances when e becomes even (prefetch)
         e++;
         if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
         const int kpn = ((e & 1) ? Ch : 0) + kc;
         const double2 Akn = sA[kpn], Bkn = sB[kpn];
-        double f1 = B1.y, f2 = B2.y;
-        if constexpr (decltype(masked)::value) {
-          f1 = (t < un.c1) ? B1.y : 0.0;
-          f2 = (t >= un.t2lo && t < un.c2) ? B2.y : 0.0;
-        }
+        const double f1 = (t < un.c1) ? B1.y : 0.0;                       // zero for the triplets this lane must skip
+        const double f2 = (t >= un.t2lo && t < un.c2) ? B2.y : 0.0;
         angular_accumulate<NTSF>(S, fma(A1.x, Ak.x, fma(A1.y, Ak.y, B1.x * Bk.x)), f1 * Bk.y);   // pair_annp.cpp:671-678
         angular_accumulate<NTSF>(S, fma(A2.x, Ak.x, fma(A2.y, Ak.y, B2.x * Bk.x)), f2 * Bk.y);
         Ak = Akn; Bk = Bkn;
       };
-      // steps [0, lo) and [hi, end) contain a triplet that some lane must skip (offset 0, or past the end of the lane's
-      // range): masked body; steps [lo, hi) are complete on every lane: mask-free body, unrolled twice
-#if ANNP_SPLIT_VARIANT == 0
-#pragma unroll 1
-      for (; t < rg.lo; t++) step(std::true_type{});
-#pragma unroll 1
-      for (; t < rg.hi; t++) step(std::false_type{});
-#pragma unroll 1
-      for (; t < rg.end; t++) step(std::true_type{});
-#elif ANNP_SPLIT_VARIANT == 1
-      // one instance of each body: phase 0 = masked head, then the complete steps two at a time; phase 1 = masked tail
-#pragma unroll 1
-      for (int ph = 0; ph < 2; ph++) {
-        const int stop = ph ? rg.end : rg.lo;
-#pragma unroll 1
-        for (; t < stop; t++) step(std::true_type{});
-        if (ph == 0) {
-#pragma unroll 1
-          for (; t + 1 < rg.hi; t += 2) { step(std::false_type{}); step(std::false_type{}); }
-        }
-      }
-#else
-#pragma unroll 1
-      for (; t < rg.end; t++) step(std::true_type{});
-#endif
+      ANNP_STEP_UNROLL
+      for (; t < end; t++) step();
     }
     // warp reduction (fixed butterfly order -> deterministic), scaling and centring (pair_annp.cpp:178-180)
 #pragma unroll
@@ -535,9 +505,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
     // ------------------------------------------------------------------ 4. angular moments (backward)
     for (int pass = 0; pass < sch.npass; pass++) {
       const Unit un = make_unit(sch, pass, lane);
-      const StepRange rg = make_range(un);
+      const int end = pass_end(un);
       double2 A1 = sA[un.m], B1 = sB[un.m], A2 = sA[Ch + un.m], B2 = sB[Ch + un.m];
-      if (!un.active) { A1 = B1 = A2 = B2 = make_double2(0.0, 0.0); }
       double v1x = 0, v1y = 0, v1z = 0, a1 = 0;
       double v2x = 0, v2y = 0, v2z = 0, a2 = 0;
       int e = un.elo;
@@ -546,7 +515,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
       int kp = ((e & 1) ? Ch : 0) + kc;
       double2 Ak = sA[kp], Bk = sB[kp];
       int t = 0;
-      auto step = [&](auto masked) {
+      auto step = [&]() {
         // this step's partner accumulators: only this lane touches them until the next __syncwarp
         double2 pa = accA[kp], pb = accB[kp];
         // next step's partner (read-only data, prefetched across the barrier)
@@ -554,12 +523,9 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
         const int kpn = ((e & 1) ? Ch : 0) + kc;
         const double2 Akn = sA[kpn], Bkn = sB[kpn];
-        double f1 = B1.y, f2 = B2.y, g1 = Bk.y, g2 = Bk.y;               // fc_j, fc_k
-        if constexpr (decltype(masked)::value) {                         // zero for the triplets this lane must skip
-          const bool ok1 = t < un.c1, ok2 = (t >= un.t2lo && t < un.c2);
-          f1 = ok1 ? B1.y : 0.0; f2 = ok2 ? B2.y : 0.0;
-          g1 = ok1 ? Bk.y : 0.0; g2 = ok2 ? Bk.y : 0.0;
-        }
+        const bool ok1 = t < un.c1, ok2 = (t >= un.t2lo && t < un.c2);
+        const double f1 = ok1 ? B1.y : 0.0, f2 = ok2 ? B2.y : 0.0;      // fc_j, zero for the triplets this lane must skip
+        const double g1 = ok1 ? Bk.y : 0.0, g2 = ok2 ? Bk.y : 0.0;      // fc_k
         const double cta = fma(A1.x, Ak.x, fma(A1.y, Ak.y, B1.x * Bk.x));
         const double ctb = fma(A2.x, Ak.x, fma(A2.y, Ak.y, B2.x * Bk.x));
         // Horner with derivative in z = cos(theta):  d <- d z + b ; b <- b z + a_k   (A = b, A'(y)/2 = d)
@@ -593,29 +559,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_force_kernel(const ForceA
         __syncwarp();
         kp = kpn; Ak = Akn; Bk = Bkn;
       };
-#if ANNP_SPLIT_VARIANT == 0
-#pragma unroll 1
-      for (; t < rg.lo; t++) step(std::true_type{});
-#pragma unroll 1
-      for (; t < rg.hi; t++) step(std::false_type{});
-#pragma unroll 1
-      for (; t < rg.end; t++) step(std::true_type{});
-#elif ANNP_SPLIT_VARIANT == 1
-      // one instance of each body: phase 0 = masked head, then the complete steps two at a time; phase 1 = masked tail
-#pragma unroll 1
-      for (int ph = 0; ph < 2; ph++) {
-        const int stop = ph ? rg.end : rg.lo;
-#pragma unroll 1
-        for (; t < stop; t++) step(std::true_type{});
-        if (ph == 0) {
-#pragma unroll 1
-          for (; t + 1 < rg.hi; t += 2) { step(std::false_type{}); step(std::false_type{}); }
-        }
-      }
-#else
-#pragma unroll 1
-      for (; t < rg.end; t++) step(std::true_type{});
-#endif
+      ANNP_STEP_UNROLL
+      for (; t < end; t++) step();
       // flush the row side; the same row pair can sit in several lanes (segments) -> one segment at a time
       for (int g = 0; g < sch.Q; g++) {
         if (un.active && un.seg == g) {
