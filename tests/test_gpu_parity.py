@@ -71,6 +71,21 @@ def test_scatter_modes_agree(name, fe_pot_file):
     pair.clear()
 
 
+def test_fixed_point_scatter_refuses_non_finite_forces(fe_pot_file):
+    """A NaN position gives NaN pair forces: the fixed-point accumulation must fail the call (ANNP_B200_EOVERFLOW), not
+    add garbage; the handle stays usable afterwards."""
+    cfg, elems, ref = util.load_case("bcc4_perturbed")
+    pair = make_pair(fe_pot_file, elems)
+    x_bad = cfg.x.copy()
+    x_bad[3, 1] = np.nan
+    with pytest.raises(capi.AnnpError) as ei:
+        pair.compute(1, 0, cfg, ago=0, x=x_bad)
+    assert ei.value.code == capi.EOVERFLOW and "fixed-point" in str(ei.value)
+    f = pair.compute(1, 0, cfg, ago=1)
+    assert np.abs(f - ref["f"]).max() <= TOL_F
+    pair.clear()
+
+
 def test_against_live_oracle_random_configuration(fe_pot_file):
     from oracle import restatement
     x, box = L.bcc(5, 4, 3)
