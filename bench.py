@@ -38,7 +38,7 @@ A_FE = 2.8553
 RC = 6.5
 SKIN = 2.0
 FLOP_TRIPLET, FLOP_PAIR, FLOP_MLP = 278.0, 168.0, 1560.0     # F_alg = 278 T + 168 N + 1560
-NCU_TRAFFIC_BYTES = 5.588e8                                  # profiles/r1c_force_kernel.md: 522.7 MB read + 36.1 MB written per launch
+NCU_TRAFFIC_BYTES = 5.558e8                                  # profiles/r1c_force_kernel.md: 522.7 MB read + 33.2 MB written per launch
 PUBLISHED_ATOM_STEPS_PER_S = 152880 * 1000 / 1789.44         # BASELINE.md section 1 (the reference's own 2-GPU log)
 
 
