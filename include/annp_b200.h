@@ -350,10 +350,10 @@ int annp_b200_set_timing(annp_b200_handle h, int enabled);
  * deterministic (no floating-point atomics):
  *   ANNP_B200_SCATTER_FIXED   every pair force is rounded to a multiple of 2^-43 eV/A (1.1e-13) and added to a 64-bit
  *                             integer accumulator per atom with integer atomics - exact and order independent, no
- *                             per-list-entry buffer in HBM.  Default for the Chebyshev ANNP and the ANNA-ADP styles.  A pair
- *                             force that is NaN or >= 2^18 eV/A makes the compute call fail with ANNP_B200_EOVERFLOW.
+ *                             per-list-entry buffer in HBM.  Default.  A pair force that is NaN or >= 2^18 eV/A makes the
+ *                             compute call fail with ANNP_B200_EOVERFLOW.
  *   ANNP_B200_SCATTER_GATHER  pair forces are stored per list entry (32 B each) and summed per atom in list order by a
- *                             gather over a reverse map (plain FP64 sums).  The Ni copy always uses this one.           */
+ *                             gather over a reverse map (plain FP64 sums).                                              */
 #define ANNP_B200_SCATTER_GATHER 0
 #define ANNP_B200_SCATTER_FIXED 1
 int annp_b200_set_scatter(annp_b200_handle h, int mode);

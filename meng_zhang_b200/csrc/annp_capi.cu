@@ -112,8 +112,8 @@ struct annp_b200_handle_s {
   DevBuf d_cell_of, d_cell_cnt, d_cell_off, d_cell_atoms, d_row_cnt, d_small;
   // per-step
   DevBuf d_xq, d_fpair, d_facc, d_fself, d_vir_c, d_vpair, d_partial, d_counters, d_engvir, d_Gdbg, d_dEdbg;
-  // how neighbour forces reach f: 1 = fixed-point integer atomics into d_facc (Chebyshev ANNP, ANNA-ADP: default),
-  // 0 = per-entry pair forces (d_fpair) summed by an ordered gather over the reverse map (Ni copy; selectable for the others)
+  // how neighbour forces reach f: 1 = fixed-point integer atomics into d_facc (default),
+  // 0 = per-entry pair forces (d_fpair) summed by an ordered gather over the reverse map (annp_b200_set_scatter)
   int scatter_fixed = 0;
   bool have_reverse = false;
   // host-mode staging
@@ -515,7 +515,7 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
   }
   rc = upload_params(h, p->weights, p->bias, !ni, err, errlen);
   if (rc) { annp_b200_clear(h); return rc; }
-  h->scatter_fixed = ni ? 0 : 1;
+  h->scatter_fixed = 1;
   *out = h;
   return ANNP_B200_OK;
 }
@@ -810,8 +810,6 @@ int annp_b200_get_stats(annp_b200_handle h, annp_b200_stats *out) {
 
 int annp_b200_set_scatter(annp_b200_handle h, int mode) {
   if (!h || (mode != ANNP_B200_SCATTER_GATHER && mode != ANNP_B200_SCATTER_FIXED)) return ANNP_B200_EINVAL;
-  if (mode == ANNP_B200_SCATTER_FIXED && h->hp.variant == ANNP_B200_VARIANT_NI)
-    return fail(h, ANNP_B200_EINVAL, "the Ni kernels write per-entry pair forces: only ANNP_B200_SCATTER_GATHER is available");
   h->scatter_fixed = mode == ANNP_B200_SCATTER_FIXED;
   return ANNP_B200_OK;
 }

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kWarps * 32) annp_bp_force_kernel(const ForceA
         sN[slot] = nb;
         spos[slot] = q;
       } else if (valid) {
-        a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (!a.facc) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
         if (a.vpair) {
           double *vp = a.vpair + (size_t) (p0 + q) * 6;
 #pragma unroll
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kWarps * 32) annp_bp_force_kernel(const ForceA
     }
     if (N > C) {
       if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
-      for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (!a.facc) for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
       __syncwarp();
       continue;
     }
@@ -259,7 +259,11 @@ __global__ void __launch_bounds__(kWarps * 32) annp_bp_force_kernel(const ForceA
       }
       const double Fx = -gx, Fy = -gy, Fz = -gz;       // Fj of the reference before CFFORCE
       const int q = spos[s];
-      a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
+      if (a.facc) {     // fixed-point scatter (annp_device.cuh); else the per-entry buffer of the ordered gather
+        if (!annp_fix_add(a.facc, a.nbr[p0 + q] & ANNP_NEIGHMASK, Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE)) atomicExch(&a.cnt->bad_force, 1);
+      } else {
+        a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
+      }
       fix -= Fx * CFFORCE; fiy -= Fy * CFFORCE; fiz -= Fz * CFFORCE;
       if (a.vir_c || a.vpair) {
         const double w0 = -ns.x * Fx, w1 = -ns.y * Fy, w2 = -ns.z * Fz, w3 = -ns.x * Fy, w4 = -ns.x * Fz, w5 = -ns.y * Fz;
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) annp_bp_fast_kernel(const Forc
         sN[slot] = g;
         spos[slot] = q;
       } else if (valid) {
-        a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (!a.facc) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
         if (a.vpair) {
           double *vp = a.vpair + (size_t) (p0 + q) * 6;
 #pragma unroll
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) annp_bp_fast_kernel(const Forc
     }
     if (N > C) {
       if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
-      for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (!a.facc) for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
       __syncwarp();
       continue;
     }
@@ -562,7 +566,11 @@ __global__ void __launch_bounds__(kWarps * 32, 3) annp_bp_fast_kernel(const Forc
       }
       const double Fx = -gx, Fy = -gy, Fz = -gz;       // Fj of the reference before CFFORCE (:180-190)
       const int q = spos[s];
-      a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
+      if (a.facc) {     // fixed-point scatter (annp_device.cuh); else the per-entry buffer of the ordered gather
+        if (!annp_fix_add(a.facc, a.nbr[p0 + q] & ANNP_NEIGHMASK, Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE)) atomicExch(&a.cnt->bad_force, 1);
+      } else {
+        a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
+      }
       fix -= Fx * CFFORCE; fiy -= Fy * CFFORCE; fiz -= Fz * CFFORCE;
       if (a.vir_c || a.vpair) {
         const double X = A.r * A.ux, Y = A.r * A.uy, Z = A.r * A.uz;
@@ -684,7 +692,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
           sN[slot] = g;
           spos[slot] = q;
         } else if (valid) {
-          a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+          if (!a.facc) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
           if (a.vpair) {
             double *vp = a.vpair + (size_t) (p0 + q) * 6;
 #pragma unroll
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
     }
     if (N > C) {
       if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
-      for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
+      if (!a.facc) for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
       __syncwarp();
       continue;
     }
@@ -881,7 +889,11 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
       const BpGeom A = sN[lane];
       const double Fx = -gx, Fy = -gy, Fz = -gz;        // Fj of the reference before CFFORCE (:180-190)
       const int q = spos[lane];
-      a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
+      if (a.facc) {     // fixed-point scatter (annp_device.cuh); else the per-entry buffer of the ordered gather
+        if (!annp_fix_add(a.facc, a.nbr[p0 + q] & ANNP_NEIGHMASK, Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE)) atomicExch(&a.cnt->bad_force, 1);
+      } else {
+        a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
+      }
       fix = -Fx * CFFORCE; fiy = -Fy * CFFORCE; fiz = -Fz * CFFORCE;
       if (a.vir_c || a.vpair) {
         const double X = A.r * A.ux, Y = A.r * A.uy, Z = A.r * A.uz;

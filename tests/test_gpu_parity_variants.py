@@ -51,6 +51,11 @@ def test_ni_golden_case(name, kernel, ni_pot_file):
     f2 = pair.compute(3, 1 + 4, cfg, ago=1)
     assert np.array_equal(f, f2)                       # deterministic
     assert np.array_equal(f, pair.compute(0, 0, cfg, ago=1))
+    # the ordered-gather scatter gives the same forces to the fixed-point resolution, and the same golden parity
+    pair.set_scatter(capi.SCATTER_GATHER)
+    fg = pair.compute(3, 1 + 4, cfg, ago=1)
+    assert np.abs(fg - f).max() <= 2e-11 and np.abs(fg - ref["f"]).max() <= 1e-9
+    assert np.array_equal(fg, pair.compute(0, 0, cfg, ago=1))
     pair.clear()
 
 
@@ -68,6 +73,9 @@ def test_anna_golden_case(name, anna_pot_file):
     f2 = pair.compute(3, 1 + 4, cfg, ago=1)
     assert np.array_equal(f, f2)
     assert np.array_equal(f, pair.compute(0, 0, cfg, ago=1))
+    pair.set_scatter(capi.SCATTER_GATHER)
+    fg = pair.compute(3, 1 + 4, cfg, ago=1)
+    assert np.abs(fg - f).max() <= 2e-11 and np.abs(fg - ref["f"]).max() <= 1e-9
     pair.clear()
 
 
