@@ -503,6 +503,10 @@ __global__ void __launch_bounds__(kWarps * 32, ANNP_MINBLOCKS) annp_force_kernel
     __syncwarp();
 
     // ------------------------------------------------------------------ 4. angular moments (backward)
+    // the monomial coefficients live in registers for the whole backward pass (read two at a time)
+    double akv[NTSF + 1];
+#pragma unroll
+    for (int i = 0; i < (NTSF + 1) / 2; i++) { const double2 c2 = coefT[i]; akv[2 * i] = c2.x; akv[2 * i + 1] = c2.y; }
     for (int pass = 0; pass < sch.npass; pass++) {
       const Unit un = make_unit(sch, pass, lane);
       const int end = pass_end(un);
@@ -529,11 +533,7 @@ __global__ void __launch_bounds__(kWarps * 32, ANNP_MINBLOCKS) annp_force_kernel
         const double cta = fma(A1.x, Ak.x, fma(A1.y, Ak.y, B1.x * Bk.x));
         const double ctb = fma(A2.x, Ak.x, fma(A2.y, Ak.y, B2.x * Bk.x));
         // Horner with derivative in z = cos(theta):  d <- d z + b ; b <- b z + a_k   (A = b, A'(y)/2 = d)
-        // (first step folded by hand: d = a_top, b = a_top z + a_{top-1};
-        //  coefficients are read two at a time: coefT[i] = (a_2i, a_2i+1), one LDS.128 per two orders)
-        double akv[NTSF + 1];
-#pragma unroll
-        for (int i = 0; i < (NTSF + 1) / 2; i++) { const double2 c2 = coefT[i]; akv[2 * i] = c2.x; akv[2 * i + 1] = c2.y; }
+        // (first step folded by hand: d = a_top, b = a_top z + a_{top-1})
         const double atop = akv[NTSF - 1], atop1 = akv[NTSF - 2];
         double Apa = atop, Apb = atop, Aa_ = fma(atop, cta, atop1), Ab_ = fma(atop, ctb, atop1);
 #pragma unroll
