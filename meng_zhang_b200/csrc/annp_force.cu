@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(kWarps * 32, ANNP_MINBLOCKS) annp_force_kernel
       int e = un.elo;
       int kc = un.m + (e >> 1);
       if (kc >= M) kc -= M;
+      e &= 1;
       double2 Ak = sA[((e & 1) ? Ch : 0) + kc], Bk = sB[((e & 1) ? Ch : 0) + kc];
       int t = 0;
       // Block basis psi_{4b+i}(z) = T_{4b}(z) z^i in z = cos(theta): P_b = w T_{4b}(z) advances by the Chebyshev
@@ -439,9 +440,9 @@ __global__ void __launch_bounds__(kWarps * 32, ANNP_MINBLOCKS) annp_force_kernel
       // well conditioned as T_n itself (conversion rows sum to <= 25; parity stays at 1e-14 in G).
       auto step = [&]() {
         // next step: e + 1 flips the parity half; the index advances when e becomes even (prefetch)
-        e++;
-        if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
-        const int kpn = ((e & 1) ? Ch : 0) + kc;
+        kc += e; if (kc == M) kc = 0;          // (e holds only the parity of the step number)
+        e ^= 1;
+        const int kpn = (e ? Ch : 0) + kc;
         const double2 Akn = sA[kpn], Bkn = sB[kpn];
         const double f1 = (t < un.c1) ? B1.y : 0.0;                       // zero for the triplets this lane must skip
         const double f2 = (t >= un.t2lo && t < un.c2) ? B2.y : 0.0;
@@ -516,6 +517,7 @@ __global__ void __launch_bounds__(kWarps * 32, ANNP_MINBLOCKS) annp_force_kernel
       int e = un.elo;
       int kc = un.m + (e >> 1);
       if (kc >= M) kc -= M;
+      e &= 1;
       int kp = ((e & 1) ? Ch : 0) + kc;
       double2 Ak = sA[kp], Bk = sB[kp];
       int t = 0;
@@ -523,9 +525,9 @@ __global__ void __launch_bounds__(kWarps * 32, ANNP_MINBLOCKS) annp_force_kernel
         // this step's partner accumulators: only this lane touches them until the next __syncwarp
         double2 pa = accA[kp], pb = accB[kp];
         // next step's partner (read-only data, prefetched across the barrier)
-        e++;
-        if (!(e & 1)) { kc++; if (kc >= M) kc -= M; }
-        const int kpn = ((e & 1) ? Ch : 0) + kc;
+        kc += e; if (kc == M) kc = 0;          // (e holds only the parity of the step number)
+        e ^= 1;
+        const int kpn = (e ? Ch : 0) + kc;
         const double2 Akn = sA[kpn], Bkn = sB[kpn];
         const bool ok1 = t < un.c1, ok2 = (t >= un.t2lo && t < un.c2);
         const double f1 = ok1 ? B1.y : 0.0, f2 = ok2 ? B2.y : 0.0;      // fc_j, zero for the triplets this lane must skip
