@@ -38,7 +38,12 @@ A_FE = 2.8553
 RC = 6.5
 SKIN = 2.0
 FLOP_TRIPLET, FLOP_PAIR, FLOP_MLP = 278.0, 168.0, 1560.0     # F_alg = 278 T + 168 N + 1560
-NCU_TRAFFIC_BYTES = 5.558e8                                  # profiles/r1c_force_kernel.md: 522.7 MB read + 33.2 MB written per launch
+NCU_TRAFFIC_BYTES = 5.534e8                                  # profiles/r1c_force_kernel.md: 520.5 MB read + 32.9 MB written per launch
+# FP64 flops the kernel EXECUTES per atom-step at this workload, from the same capture: (2 x 7.328e9 DFMA + 0.938e9 DMUL +
+# 0.800e9 DADD warp instructions) x 30.89 active threads / 524 288 atoms.  The algorithmic count prices the
+# straightforward recompute formulation at 278 flops per triplet; the kernel needs ~150, so `frac` (algorithmic, the
+# contract's definition) can exceed 1 while the pipe itself is `executed.frac` busy with useful flops.
+NCU_EXECUTED_FLOP_PER_ATOM_STEP = 9.659e5
 PUBLISHED_ATOM_STEPS_PER_S = 152880 * 1000 / 1789.44         # BASELINE.md section 1 (the reference's own 2-GPU log)
 
 
@@ -255,6 +260,12 @@ def run_ours(args):
                          "traffic": NCU_TRAFFIC_BYTES if (cells == 64 and world == 1) else None,
                          "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / (ms_total / args.steps),
                          "flop_per_atom_step": flop_per_launch / nlocal,
+                         "executed": ({"flop_per_atom_step": NCU_EXECUTED_FLOP_PER_ATOM_STEP,
+                                       "tflops": NCU_EXECUTED_FLOP_PER_ATOM_STEP * nlocal / (kern_ms * 1e-3) / 1e12,
+                                       "frac": NCU_EXECUTED_FLOP_PER_ATOM_STEP * nlocal / (kern_ms * 1e-3) / 1e12 / peak_tf,
+                                       "note": "FP64 flops actually issued (ncu opcode counts of profiles/r1c_force_kernel.md): the algorithmic "
+                                               "count credits 278 flops per triplet, the kernel executes ~150"}
+                                      if (cells == 64 and kern_ms > 0 and peak_tf > 0) else None),
                          "peak_source": "measured on this GPU by annp_b200_fp64_peak_tflops (pure DFMA loop); "
                                         "MEASURED_PEAKS.json has no FP64 entry"},
             "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": nall * (24 + 4), "d2h_bytes_per_step": nall * 24 + 8,

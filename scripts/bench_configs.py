@@ -6,7 +6,7 @@
                periodic z, rim atoms (type 2) held fixed, NVE, decomposed over the ranks it is launched on
     anna       bcc Fe ANNA-ADP, 40^3 cells = 128 000 atoms, NVT 300 K
 
-    python scripts/bench_configs.py [--steps 100] [--only 2,3,4,anna]
+    python scripts/bench_configs.py [--steps 100] [--only 2,3,4,anna]      (ANNP_BENCH_GRAPH=1: replay the step as a CUDA graph)
     python -m torch.distributed.run --nproc-per-node 8 ... scripts/bench_configs.py --only 4
 
 One JSON line per configuration on rank 0: atom-steps/s (CUDA events, max over ranks), ms per step, temperature /
@@ -72,6 +72,12 @@ def run_case(name, kind, x_all, box, mass, periodic, ensemble, steps, rank, worl
         stepper = md.step_nh
     for _ in range(5):
         stepper()
+    graph = bool(os.environ.get("ANNP_BENCH_GRAPH")) and world == 1
+    if graph:       # the step is ~10 short kernels: replay it as one CUDA graph (single rank only, valid until the next re-neighbouring)
+        md.capture_step(nh=ensemble != "nve")
+        stepper = lambda: md.replay(1)
+        for _ in range(5):
+            stepper()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -94,7 +100,7 @@ def run_case(name, kind, x_all, box, mass, periodic, ensemble, steps, rank, worl
     if world > 1:
         dist.all_reduce(nat)
     if rank == 0:
-        print(json.dumps({"config": name, "atoms": int(nat), "n_gpus": world, "grid": "x".join(map(str, grid)), "ensemble": ensemble,
+        print(json.dumps({"config": name, "atoms": int(nat), "n_gpus": world, "grid": "x".join(map(str, grid)), "ensemble": ensemble, "cuda_graph": graph,
                           "steps": steps, "ms_per_step": ms, "atom_steps_per_s": float(nat) / (ms * 1e-3),
                           "ns_per_day": 86400.0 / (ms * 1e-3) * 1e-6, "neighbors_in_cutoff": st.avg_neigh_cut,
                           "list_neighbors_max": st.max_neigh_list, **extra}), flush=True)
