@@ -453,19 +453,35 @@ __global__ void __launch_bounds__(kWarps * 32, ANNP_MINBLOCKS) annp_force_kernel
       ANNP_STEP_UNROLL
       for (; t < end; t++) step();
     }
-    // warp reduction (fixed butterfly order -> deterministic), scaling and centring (pair_annp.cpp:178-180)
+    // warp reduction, scaling and centring (pair_annp.cpp:178-180).  All nsf <= 32 sums are reduced TOGETHER by a
+    // transposing butterfly: in the round with lane mask m every lane keeps the half of its values that belongs to its
+    // side of the mask and hands the other half over, so the number of live values halves each round (16+8+4+2+1 = 31
+    // shuffles instead of 5 per sum) and lane n ends up with the total of sum n.  Fixed order -> deterministic.
+    {
+      static_assert(NPSF + NTSF <= 32, "the transposing reduction handles at most 32 descriptor components");
+      double w[32];
 #pragma unroll
-    for (int m = 0; m < NPSF; m++) {
-      const double v = warp_sum(gr[m]);
-      if (lane == 0) sG[m] = sScale[m] * v - sScale[m] * sAvg[m];
-    }
+      for (int n = 0; n < 32; n++) w[n] = (n < NPSF) ? gr[n < NPSF ? n : 0] : (n < NPSF + NTSF ? S[(n >= NPSF && n < NPSF + NTSF) ? n - NPSF : 0] : 0.0);
 #pragma unroll
-    for (int n = 0; n < NTSF; n++) S[n] = warp_sum(S[n]);      // every lane holds the totals
-    if (lane < NTSF) {                                          // block basis -> T_n((z+1)/2), lane n
-      double v = 0.0;
+      for (int m = 16, cnt = 32; m >= 1; m >>= 1, cnt >>= 1) {
+        const bool up = (lane & m) != 0;
 #pragma unroll
-      for (int j = 0; j < NTSF; j++) v = fma(__ldg(gB2C + j * NTSF + lane), S[j], v);
-      sG[NPSF + lane] = sScale[NPSF + lane] * v - sScale[NPSF + lane] * sAvg[NPSF + lane];
+        for (int n = 0; n < cnt / 2; n++) {
+          const double send = up ? w[n] : w[n + cnt / 2];
+          const double keep = up ? w[n + cnt / 2] : w[n];
+          w[n] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      }
+      const double tot = w[0];                                  // total of component `lane`
+      if (lane < NPSF) sG[lane] = sScale[lane] * tot - sScale[lane] * sAvg[lane];
+      else if (lane < NPSF + NTSF) sdE[lane] = tot;             // block-basis sums, parked in sdE (free until stage 3)
+      __syncwarp();
+      if (lane < NTSF) {                                        // block basis -> T_n((z+1)/2), lane n
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < NTSF; j++) v = fma(__ldg(gB2C + j * NTSF + lane), sdE[NPSF + j], v);
+        sG[NPSF + lane] = sScale[NPSF + lane] * v - sScale[NPSF + lane] * sAvg[NPSF + lane];
+      }
     }
     __syncwarp();
 
