@@ -1,35 +1,39 @@
 // annp_force.cu -- the fused ANNP force kernel for sm_100a.
 //
 // One warp owns one centre atom at a time (dynamic atom scheduler).  For that atom it
-//   1. filters the LAMMPS list row to the in-cutoff neighbours (ballot compaction keeps list order),
-//      caches unit vector / fc / dfc / r per neighbour in shared memory and accumulates the radial
-//      Chebyshev sums                                   (reference: pair_annp.cpp:134-153, 633-656)
-//   2. walks every unordered neighbour pair (j,k) ONCE and accumulates the 19 angular sums in
-//      registers                                        (reference: pair_annp.cpp:156-176, 658-695)
+//   1. filters the LAMMPS list row to the in-cutoff neighbours: (a) four 32-entry chunks per trip with all their loads in
+//      flight, ballot compaction keeps list order; (b) one lane per KEPT neighbour computes unit vector / fc / dfc / r
+//      into shared memory and accumulates the radial Chebyshev sums
+//                                                       (reference: pair_annp.cpp:134-153, 633-656)
+//   2. walks every unordered neighbour pair (j,k) ONCE and accumulates the angular sums in registers, in the block basis
+//      T_4b(z) z^i of z = cos(theta) (one accumulate per order); all nsf sums are then reduced across the warp together
+//      (transposing butterfly) and converted to the reference's T_n((z+1)/2)
+//                                                       (reference: pair_annp.cpp:156-176, 658-695)
 //   3. runs the element's MLP forward and reverse-mode backprop -> E_i and dE/dG
 //                                                       (reference: pair_annp.cpp:741-804)
 //   4. walks the pairs a second time, evaluating  A(y) = sum_n c_n T_n(y) and A'(y)  by Horner's rule in
-//      z = cos(theta) (2 FMA per order; c is converted to monomial coefficients once per atom) and
+//      z = cos(theta) (2 FMA per order; c is converted to monomial coefficients once per atom, held in registers) and
 //      accumulating, per neighbour, the four moments
 //          V = sum_k P u_k,  Aa = sum_k A fc_k     (P = A'/2 fc_j fc_k;  S = sum_k P cos(theta) = u_j . V)
 //      so dG/dx is never materialised and no floating-point atomics are used
 //   5. turns the moments into the force on every neighbour, F_j = -e_scale dOut/dx_j
-//      (reference: pair_annp.cpp:191-200), writes it at the neighbour's LIST position (a later
-//      gather kernel sums them per atom in a fixed order), and reduces F_i = -sum F_j, the
-//      per-centre virial and the energy.
+//      (reference: pair_annp.cpp:191-200), and scatters it: FIXED = true adds it to the neighbour's fixed-point
+//      accumulator with 64-bit integer atomics (exact, order independent), FIXED = false writes it at the neighbour's
+//      LIST position for a later ordered gather; reduces F_i = -sum F_j, the per-centre virial and the energy.
 //
 // Pair schedule of passes 2 and 4 ("row-pair circulant").  The N neighbours are padded to an even
 // count Np = 2M with a zero-weight dummy.  A lane owns the ROW PAIR (2m, 2m+1) and steps e = 1..M+1;
 // in step e it meets the single partner k = (2m + e) mod Np with both of its rows: triplet (2m, k)
 // has circulant offset e, triplet (2m+1, k) offset e-1, and offsets 1..M (the last one only for
 // rows < M) enumerate every unordered pair exactly once.  Consequences:
-//   * two independent Chebyshev recurrences per lane are in flight (latency hiding on the FP64 pipe)
+//   * two independent triplets per lane are in flight (latency hiding on the FP64 pipe)
 //   * the partner's data is loaded once, and its accumulators are updated once, per TWO triplets
 //   * rows are stored parity-split (even rows first), so the partners of consecutive lanes are
 //     consecutive shared-memory words: conflict-free 128-bit accesses, and all lanes of a step
 //     touch DISTINCT partners, which makes the plain read-modify-write race free and the
 //     summation order fixed (bit-reproducible results)
-//   * the step range is cut into Q segments so that M*Q work units fill the 32 lanes evenly.
+//   * the step range is cut into Q segments so that M*Q work units fill the 32 lanes evenly; a pass stops at the last
+//     step any of its lanes needs.
 //
 // All arithmetic is IEEE FP64 (the reference CPU pair style is the parity target); the kernel is bound
 // by the FP64 FMA pipe, see DESIGN.md.
