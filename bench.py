@@ -38,12 +38,12 @@ A_FE = 2.8553
 RC = 6.5
 SKIN = 2.0
 FLOP_TRIPLET, FLOP_PAIR, FLOP_MLP = 278.0, 168.0, 1560.0     # F_alg = 278 T + 168 N + 1560
-NCU_TRAFFIC_BYTES = 5.534e8                                  # profiles/r1c_force_kernel.md: 520.5 MB read + 32.9 MB written per launch
-# FP64 flops the kernel EXECUTES per atom-step at this workload, from the same capture: (2 x 7.328e9 DFMA + 0.938e9 DMUL +
-# 0.800e9 DADD warp instructions) x 30.89 active threads / 524 288 atoms.  The algorithmic count prices the
+NCU_TRAFFIC_BYTES = 5.563e8                                  # profiles/r1c_force_kernel.md: 521.7 MB read + 34.7 MB written per launch
+# FP64 flops the kernel EXECUTES per atom-step at this workload, from the same capture: (2 x 7.324e9 DFMA + 0.934e9 DMUL +
+# 0.743e9 DADD warp instructions) x 30.87 active threads / 524 288 atoms.  The algorithmic count prices the
 # straightforward recompute formulation at 278 flops per triplet; the kernel needs ~150, so `frac` (algorithmic, the
 # contract's definition) can exceed 1 while the pipe itself is `executed.frac` busy with useful flops.
-NCU_EXECUTED_FLOP_PER_ATOM_STEP = 9.659e5
+NCU_EXECUTED_FLOP_PER_ATOM_STEP = 9.612e5
 PUBLISHED_ATOM_STEPS_PER_S = 152880 * 1000 / 1789.44         # BASELINE.md section 1 (the reference's own 2-GPU log)
 
 
@@ -71,7 +71,7 @@ class ClockSampler:
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -81,19 +81,28 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
+        # nvidia-smi block-buffers its output when it writes to a pipe, so lines ARRIVE in bursts: each sample is placed
+        # by nvidia-smi's own timestamp column (same host clock as time.time()); arrival time is only the fallback
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+            cols = [c.strip() for c in line.split(",")]
+            t = time.time()
+            try:
+                t = datetime.datetime.strptime(cols[7], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except (IndexError, ValueError):
+                pass
+            self.rows.append((t, cols))
 
     def mark_begin(self):
-        self.t0 = time.perf_counter()
+        self.t0 = time.time()
 
     def mark_end(self):
-        self.t1 = time.perf_counter()
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
