@@ -362,6 +362,12 @@ int annp_b200_set_scatter(annp_b200_handle h, int mode);
  * test hook replacing the reference's printf debugging). Either pointer may be NULL. */
 int annp_b200_debug_descriptors(annp_b200_handle h, double *G, double *dE_dG);
 
+/* Host arithmetic, no device needed: the two basis-conversion matrices of the angular passes, each [ntsf][ntsf] row-major
+ * (ntsf <= 24).  With y = (z+1)/2, z = cos(theta) and psi_{4b+i}(z) = T_{4b}(z) z^i:
+ *     T_n(y) = sum_k cheb2mono[k*ntsf + n] z^k = sum_j blk2cheb[j*ntsf + n] psi_j(z)
+ * (the reference evaluates T_n(y) by recurrence, fe_v2/src/pair_annp.cpp:596-611,658-695).  Exposed for tests. */
+int annp_b200_basis_matrices(int ntsf, double *cheb2mono, double *blk2cheb);
+
 int annp_b200_abi_version(void);
 /* number of CUDA devices visible to the library (0 = none, no error) */
 int annp_b200_device_count(void);

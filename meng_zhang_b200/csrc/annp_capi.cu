@@ -414,56 +414,14 @@ static int upload_params(annp_b200_handle h, const double *weights, const double
   hp.weights = h->d_weights.as<double>();
   hp.bias = h->d_bias.as<double>();
   if (chebyshev) {
-    // T_n(y) with y = (z+1)/2 written in powers of z = cos(theta): the backward pass evaluates the angular
-    // polynomial and its derivative by Horner's rule in z.  All intermediate numbers are dyadic rationals
-    // that long double holds exactly for the supported orders.
+    // the two basis-conversion matrices of the angular passes (host arithmetic: annp_b200_basis_matrices)
     const int nt = hp.ntsf;
-    if (nt > 24) return bail(cudaErrorInvalidValue, "ntsf > 24 is not supported by the monomial conversion");
-    std::vector<long double> T((size_t) nt * nt, 0.0L), M((size_t) nt * nt, 0.0L);   // T[n][k]: coefficient of y^k
-    for (int n = 0; n < nt; n++) {
-      if (n == 0) T[0] = 1.0L;
-      else if (n == 1) T[(size_t) nt + 1] = 1.0L;
-      else
-        for (int k = 0; k < nt; k++)
-          T[(size_t) n * nt + k] = (k > 0 ? 2.0L * T[(size_t) (n - 1) * nt + k - 1] : 0.0L) - T[(size_t) (n - 2) * nt + k];
-    }
-    std::vector<long double> pw(nt, 0.0L), nx(nt, 0.0L);     // ((z+1)/2)^k in powers of z
-    pw[0] = 1.0L;
-    for (int k = 0; k < nt; k++) {
-      for (int n = 0; n < nt; n++)
-        for (int q = 0; q <= k; q++) M[(size_t) q * nt + n] += T[(size_t) n * nt + k] * pw[q];
-      std::fill(nx.begin(), nx.end(), 0.0L);
-      for (int q = 0; q <= k && q + 1 < nt; q++) { nx[q] += 0.5L * pw[q]; nx[q + 1] += 0.5L * pw[q]; }
-      pw = nx;
-    }
-    std::vector<double> Md((size_t) nt * nt);
-    for (size_t q = 0; q < Md.size(); q++) Md[q] = (double) M[q];
+    std::vector<double> Md((size_t) nt * nt), Xd((size_t) nt * nt);
+    if (annp_b200_basis_matrices(nt, Md.data(), Xd.data()) != ANNP_B200_OK)
+      return bail(cudaErrorInvalidValue, "ntsf > 24 is not supported by the monomial conversion");
     if ((e = h->d_cheb2mono.reserve(sizeof(double) * Md.size(), 1.0)) != cudaSuccess) return bail(e, "cudaMalloc cheb2mono");
     if ((e = cudaMemcpy(h->d_cheb2mono.p, Md.data(), sizeof(double) * Md.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload cheb2mono");
     hp.cheb2mono = h->d_cheb2mono.as<double>();
-    // Forward pass basis psi_{4b+i}(z) = T_{4b}(z) z^i (annp_force.cu, stage 2): blk2cheb[j*nt+n] = X[j][n] with
-    // T_n((z+1)/2) = sum_j X[j][n] psi_j(z).  psi_j has degree exactly j, so the monomial matrix of the basis is upper
-    // triangular with power-of-two diagonal: back substitution in long double.
-    std::vector<long double> Tz((size_t) nt * nt, 0.0L), Bm((size_t) nt * nt, 0.0L), X((size_t) nt * nt, 0.0L);   // Tz[n][k]: coeff of z^k in T_n(z)
-    for (int n = 0; n < nt; n++) {
-      if (n == 0) Tz[0] = 1.0L;
-      else if (n == 1) Tz[(size_t) nt + 1] = 1.0L;
-      else
-        for (int k = 0; k < nt; k++)
-          Tz[(size_t) n * nt + k] = (k > 0 ? 2.0L * Tz[(size_t) (n - 1) * nt + k - 1] : 0.0L) - Tz[(size_t) (n - 2) * nt + k];
-    }
-    for (int j = 0; j < nt; j++) {          // Bm[k][j]: coefficient of z^k in psi_j
-      const int b4 = (j / 4) * 4, i = j % 4;
-      for (int k = 0; k + i < nt && k <= b4; k++) Bm[(size_t) (k + i) * nt + j] = Tz[(size_t) b4 * nt + k];
-    }
-    for (int n = 0; n < nt; n++)
-      for (int j = nt - 1; j >= 0; j--) {
-        long double acc = M[(size_t) j * nt + n];
-        for (int q = j + 1; q < nt; q++) acc -= Bm[(size_t) j * nt + q] * X[(size_t) q * nt + n];
-        X[(size_t) j * nt + n] = acc / Bm[(size_t) j * nt + j];
-      }
-    std::vector<double> Xd((size_t) nt * nt);
-    for (size_t q = 0; q < Xd.size(); q++) Xd[q] = (double) X[q];
     if ((e = h->d_blk2cheb.reserve(sizeof(double) * Xd.size(), 1.0)) != cudaSuccess) return bail(e, "cudaMalloc blk2cheb");
     if ((e = cudaMemcpy(h->d_blk2cheb.p, Xd.data(), sizeof(double) * Xd.size(), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "upload blk2cheb");
     hp.blk2cheb = h->d_blk2cheb.as<double>();

@@ -164,3 +164,41 @@ def test_nose_hoover_host_twin_conserves_the_extended_energy(p_flag):
         assert nh.boxhi[0] - nh.boxlo[0] == box[0] and nh.boxhi[2] - nh.boxlo[2] == box[2]    # uncoupled edges fixed
         assert np.ptp(ly) > 1e-3                                                                # coupled edge breathes
         assert abs(np.mean(nh.p_current[1])) < 3000.0                                           # bar, near the 0 target
+
+
+@pytest.mark.parametrize("ntsf", [6, 19, 20, 24])
+def test_angular_basis_conversion_matrices(ntsf):
+    """The kernel evaluates the reference's T_n((cos theta + 1)/2) (fe_v2/src/pair_annp.cpp:596-611, 671) in two other
+    bases of z = cos theta: monomials (backward Horner) and psi_{4b+i} = T_{4b}(z) z^i (forward accumulation).  Both
+    conversion matrices are host arithmetic (annp_b200_basis_matrices): check the identities against the recurrence the
+    reference uses, and the conditioning that makes the block basis as accurate as the recurrence."""
+    import ctypes as C
+    from meng_zhang_b200 import capi
+    from numpy.polynomial import chebyshev as Ch
+    lib = capi.lib()
+    c2m = np.zeros((ntsf, ntsf))
+    b2c = np.zeros((ntsf, ntsf))
+    assert lib.annp_b200_basis_matrices(ntsf, c2m.ctypes.data_as(capi.c_double_p), b2c.ctypes.data_as(capi.c_double_p)) == 0
+    z = np.linspace(-1.0, 1.0, 401).astype(np.longdouble)
+    y = (z + 1) / 2
+
+    def cheb_rec(x, n):          # the reference's recurrence (annp_Tx)
+        t0, t1 = np.ones_like(x), x.copy()
+        if n == 0:
+            return t0
+        for _ in range(n - 1):
+            t0, t1 = t1, 2 * x * t1 - t0
+        return t1
+
+    T_ref = np.stack([cheb_rec(y, n) for n in range(ntsf)])                       # [n][sample]
+    mono = np.stack([z ** k for k in range(ntsf)])                                # [k][sample]
+    psi = np.stack([cheb_rec(z, 4 * (j // 4)) * z ** (j % 4) for j in range(ntsf)])
+    assert np.abs(c2m.astype(np.longdouble).T @ mono - T_ref).max() < 1e-13
+    assert np.abs(b2c.astype(np.longdouble).T @ psi - T_ref).max() < 1e-15
+    # conditioning: |columns| of the block-basis conversion sum to a few tens, those of the monomial one to ~1e4
+    assert np.abs(b2c).sum(axis=0).max() < 40.0
+    if ntsf >= 19:
+        assert np.abs(c2m).sum(axis=0).max() > 1e3
+    # entries are dyadic rationals: the first rows are plain Chebyshev structure (T_0 = 1, T_1 = (z+1)/2)
+    assert c2m[0, 0] == 1.0 and c2m[0, 1] == 0.5 and c2m[1, 1] == 0.5
+    assert lib.annp_b200_basis_matrices(25, c2m.ctypes.data_as(capi.c_double_p), b2c.ctypes.data_as(capi.c_double_p)) == capi.EINVAL
