@@ -26,6 +26,7 @@
 #include "suffix.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -230,6 +231,12 @@ void PairANNPB200::init_style()
   // the reference funnels init codes through GPU_EXTRA::check_flag, which aborts all ranks (line 235)
   if (rc == ANNP_B200_ENOMEM) error->all(FLERR, "Insufficient memory on accelerator");
   if (rc != 0) error->all(FLERR, std::string("annp/gpu initialisation failed: ") + msg);
+  // The input deck keeps the reference's zero-argument pair_style line; ANNP_B200_SCATTER=gather selects the ordered
+  // FP64 gather instead of the default fixed-point force accumulation (include/annp_b200.h: annp_b200_set_scatter)
+  if (const char *sc = getenv("ANNP_B200_SCATTER")) {
+    const int mode = !strcmp(sc, "gather") ? ANNP_B200_SCATTER_GATHER : (!strcmp(sc, "fixed") ? ANNP_B200_SCATTER_FIXED : -1);
+    if (mode < 0 || annp_b200_set_scatter(handle, mode) != 0) error->all(FLERR, "ANNP_B200_SCATTER must be 'fixed' or 'gather'");
+  }
 
   neighbor->add_request(this, NeighConst::REQ_FULL);
 }

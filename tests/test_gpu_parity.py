@@ -270,3 +270,15 @@ def test_lammps_pair_style_through_the_shim_driver(name, fe_pot_file):
         assert np.abs(out["virial"] - ref[vkey]).max() <= TOL_V
         if vflag & 4:
             assert np.abs(out["vatom"] - ref["vatom"]).max() <= TOL_F
+    # ANNP_B200_SCATTER (read by the pair class at init_style) switches the force accumulation; anything else is an error
+    import os
+    fixed = run_ref.run_reference("plugin_annp_b200", cfg, fe_pot_file, elems, eflag=1, vflag=0)["f"]
+    os.environ["ANNP_B200_SCATTER"] = "gather"
+    try:
+        gathered = run_ref.run_reference("plugin_annp_b200", cfg, fe_pot_file, elems, eflag=1, vflag=0)["f"]
+        os.environ["ANNP_B200_SCATTER"] = "sideways"
+        with pytest.raises(RuntimeError):
+            run_ref.run_reference("plugin_annp_b200", cfg, fe_pot_file, elems, eflag=1, vflag=0)
+    finally:
+        del os.environ["ANNP_B200_SCATTER"]
+    assert np.abs(gathered - ref["f"]).max() <= TOL_F and np.abs(gathered - fixed).max() <= 2e-11
