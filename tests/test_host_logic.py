@@ -202,3 +202,26 @@ def test_angular_basis_conversion_matrices(ntsf):
     # entries are dyadic rationals: the first rows are plain Chebyshev structure (T_0 = 1, T_1 = (z+1)/2)
     assert c2m[0, 0] == 1.0 and c2m[0, 1] == 0.5 and c2m[1, 1] == 0.5
     assert lib.annp_b200_basis_matrices(25, c2m.ctypes.data_as(capi.c_double_p), b2c.ctypes.data_as(capi.c_double_p)) == capi.EINVAL
+
+
+@pytest.mark.parametrize("fixed_point", [True, False])
+def test_kernel_arithmetic_restated_in_numpy_matches_the_oracle(fixed_point, fe_pot_file):
+    """The CUDA kernel's reformulation (block-basis forward sums, reverse-mode MLP, four-moment backward pass with
+    S = u.V, monomial Horner, fixed-point scatter), restated in numpy (tests/kernel_math_host.py), gives the reference's
+    forces and energies: the algebra is checked on the CPU, the GPU tests then only have to show that the kernel
+    implements it."""
+    import kernel_math_host as K
+    from meng_zhang_b200 import capi
+    from oracle import restatement
+    pot = read_potential(fe_pot_file, ["Fe"])
+    c2m, b2c = np.zeros((pot.ntsf, pot.ntsf)), np.zeros((pot.ntsf, pot.ntsf))
+    assert capi.lib().annp_b200_basis_matrices(pot.ntsf, c2m.ctypes.data_as(capi.c_double_p), b2c.ctypes.data_as(capi.c_double_p)) == 0
+    x, box = L.bcc(3, 3, 3)
+    cfg = L.build_config(L.perturb(x, 0.08, 31), box, 6.5)
+    ref = restatement.compute(pot, cfg, nthreads=2)
+    f, eatom = K.compute(pot, cfg, c2m, b2c, fixed_point=fixed_point)
+    assert np.abs(eatom[: cfg.nlocal] - ref["eatom"][: cfg.nlocal]).max() <= 5e-12
+    assert np.abs(f - ref["f"]).max() <= (3e-12 if fixed_point else 3e-13)       # observed 5.2e-13 / 5.4e-14, as on the GPU
+    if fixed_point:       # every pair force moved by at most half a unit of 2^-43 eV/A: <= 112 * 5.7e-14 per atom
+        f_plain, _ = K.compute(pot, cfg, c2m, b2c, fixed_point=False)
+        assert 0.0 < np.abs(f - f_plain).max() <= 120 * 0.5 * 2.0 ** -43
