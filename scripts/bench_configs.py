@@ -4,6 +4,8 @@
     config 3   bcc Fe ANNP, 40x40x80 cells = 256 000 atoms, NPT 300 K (the deck's `y 0 0 1` coupling)
     config 4   bcc Fe screw dislocation (structures.screw_dislocation((22, 38, 50)) ~ 5.1e5 atoms), free x / y surfaces,
                periodic z, rim atoms (type 2) held fixed, NVE, decomposed over the ranks it is launched on
+    config 5b  bcc Fe bicrystal with two symmetric tilt grain boundaries (structures.stgb, the reference's stgb.cpp geometry),
+               519 480 atoms = one weak-scaling cell, two LAMMPS atom types both mapped to Fe, periodic, NVE  (--only 5b)
     anna       bcc Fe ANNA-ADP, 40^3 cells = 128 000 atoms, NVT 300 K
 
     python scripts/bench_configs.py [--steps 100] [--only 2,3,4,anna]      (ANNP_BENCH_GRAPH=1: replay the step as a CUDA graph)
@@ -129,6 +131,11 @@ def main():
         xs, box, types, core = S.screw_dislocation((22, 38, 50))
         run_case("4: bcc Fe screw dislocation, free x/y, periodic z, fixed rim, NVE", "fe", xs, box, 55.845, (False, False, True), "nve",
                  a.steps, rank, world, local, dev, frozen=(types == 2))
+    if "5b" in only:      # BASELINE configs[4] variant: the weak-scaling cell filled with the reference's STGB bicrystal
+        u = S.stgb_unit_lengths()
+        xs, box, types = S.stgb(length_box=(13 * u[0], 37 * u[1], 45 * u[2]))     # 26 x 37 x 45 units = 181.8 x 183.0 x 181.7 A
+        run_case(f"5b: bcc Fe symmetric tilt grain boundaries (stgb.cpp geometry), {len(xs)} atoms, two atom types -> Fe, PBC, NVE", "fe2",
+                 xs, box, 55.845, pbc, "nve", a.steps, rank, world, local, dev, types=types)
     if "anna" in only:
         x, box = L.bcc(40, 40, 40)
         run_case("anna: bcc Fe ANNA-ADP 128 000 atoms NVT 300 K", "anna", L.perturb(x, 0.02, 3), box, 55.845, pbc, "nvt", a.steps, rank, world, local, dev)
