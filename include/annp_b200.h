@@ -36,13 +36,19 @@
 extern "C" {
 #endif
 
-#define ANNP_B200_ABI_VERSION 2
+#define ANNP_B200_ABI_VERSION 3
 
 #define ANNP_B200_MAX_SF 64        /* descriptor components                      */
 #define ANNP_B200_MAX_NOD 32       /* nodes per hidden layer                     */
 #define ANNP_B200_MAX_LAYERS 6     /* weight layers (ntl - 1)                    */
 #define ANNP_B200_MAX_ELEMENTS 4
 #define ANNP_B200_MAX_NEIGH 384    /* in-cutoff neighbours of one atom (smem tile) */
+/* Chebyshev descriptor shapes (Fe copies, ANNA-ADP): any 1 <= npsf <= 16, 1 <= ntsf <= 24 (the reference's CPU style reads any
+ * `TL HL nodes nsf npsf ntsf` line, fe_v2/src/pair_annp.cpp:367-389).  (9,19), (8,20), (4,6) have exact kernel instantiations;
+ * every other shape runs zero-padded on (8,24) or (16,24).  ntsf stops at 24 because the angular polynomial is evaluated in
+ * monomial form, which is well conditioned up to degree 23.  All five activations of each copy, nelements <= 4. */
+#define ANNP_B200_MAX_NPSF 16
+#define ANNP_B200_MAX_NTSF 24
 
 /* error codes */
 #define ANNP_B200_OK 0
@@ -222,7 +228,28 @@ int annp_b200_neigh(annp_b200_handle h, int inum, int nall, const int *ilist, co
 int annp_b200_neigh_csr(annp_b200_handle h, int inum, int nall, const int *ilist, const int64_t *offsets,
                         const int *neigh);
 
+/* Device-neighbour mode of the host-driven style (the reference's GPU_NEIGH path annp_gpu_compute_n,
+ * fe/lib/lal_annp.cpp:376-498: `package gpu ... neigh yes`): build the full list on the device from HOST positions
+ * x [nall][3] (atoms 0..nlocal-1 are centres); bbox_lo / bbox_hi bound all nall positions (sub-domain +- ghost cutoff).
+ * Replaces annp_b200_neigh at neighbor->ago == 0; annp_b200_compute follows as usual. */
+int annp_b200_neigh_build_host(annp_b200_handle h, int nlocal, int nall, const double *x, const double *bbox_lo,
+                               const double *bbox_hi, double cutneigh);
+
+/* Page-locking of caller-owned host arrays.  annp_b200_compute copies x / type in and f / eatom / vatom out with
+ * cudaMemcpyAsync: from pageable memory the driver stages every copy through its own bounce buffer (a few GB/s and a
+ * synchronous hand-over); from page-locked memory it is one DMA at PCIe speed.  LAMMPS allocates atom->x / atom->f with
+ * malloc, so the pair style registers them once per (re)allocation (atom->nmax growth) - host_register on a range that is
+ * already registered is a no-op - and allocates its own staging arrays with host_alloc.  (The reference's LAL layer keeps
+ * page-locked staging arrays of its own: UCL_H_Vec in lal_atom.h / lal_answer.h of LAMMPS' lib/gpu.) */
+int annp_b200_host_register(void *ptr, size_t bytes);
+int annp_b200_host_unregister(void *ptr);
+void *annp_b200_host_alloc(size_t bytes);
+void annp_b200_host_free(void *ptr);
+
 /* One Pair::compute.  x is [nall][3], type [nall] (1-based); outputs may be NULL when not requested.
+ *   type    may be NULL on the calls between two neighbour-list builds: the types uploaded by the last call that
+ *           passed them are reused (atoms keep their slots until the next re-neighbouring; the reference uploads x and
+ *           type together every step, lal_annp.cpp:310-312)
  *   f       [nall][3]  ASSIGNED (not accumulated), like the reference (lal_annp.cpp:336-347); ghost
  *                      rows carry the contributions LAMMPS reverse-communicates to the owners
  *   eng     sum of atomic energies of the inum centre atoms (eng_vdwl)
@@ -342,8 +369,19 @@ typedef struct annp_b200_stats {
                                 compute call issued with timing enabled, else 0 */
   double force_kernel_ms_total; /* sum of the CUDA-event times of the force kernel over the (up to 256)  */
   int force_kernel_samples;     /* ... timed launches since annp_b200_set_timing(h, 1)                    */
+  /* ---- ABI 3 ---- */
+  long long overflow_pass_atoms;/* atoms redone by the overflow pass (in-cutoff neighbours outgrew the first-pass shared-memory
+                                   tile between two list builds) since the previous get_stats / host-mode compute          */
+  int tile_capacity;            /* neighbour slots of the first-pass tile                                                   */
+  double stage_cycles[8];       /* libraries built with -DANNP_STAGE_CLOCKS: SM cycles summed over warps since the previous
+                                   call, per stage: 0 filter, 1 radial, 2 forward angular, 3 reduction + MLP, 4 backward
+                                   angular, 5 force assembly + scatter, 6 scheduler; zeros otherwise                        */
 } annp_b200_stats;
-int annp_b200_get_stats(annp_b200_handle h, annp_b200_stats *out);   /* synchronises the device */
+/* Synchronises the device.  Also the error check of the device-resident mode: returns ANNP_B200_EOVERFLOW if, in any
+ * annp_b200_compute_device since the previous call, an atom had more than ANNP_B200_MAX_NEIGH in-cutoff neighbours or a
+ * pair force left the fixed-point range (the flags are sticky on the device until read here).  Atoms that merely outgrow
+ * the first-pass tile are NOT an error: the overflow pass redoes them inside the same step. */
+int annp_b200_get_stats(annp_b200_handle h, annp_b200_stats *out);
 int annp_b200_set_timing(annp_b200_handle h, int enabled);
 
 /* How the forces on the NEIGHBOURS of a centre atom (f[j] += Fj, fe_v2/src/pair_annp.cpp:198-200) reach f.  Both are

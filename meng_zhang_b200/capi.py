@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ANNP_B200_LIB") or os.path.join(HERE, "lib", "libannp_b200.so")
 
 MAX_SF, MAX_NOD, MAX_LAYERS, MAX_ELEMENTS, MAX_NEIGH = 64, 32, 6, 4, 384
-ABI_VERSION = 2
+ABI_VERSION = 3
 VARIANT_FE, VARIANT_NI, VARIANT_ANNA_ADP = 0, 1, 2
 MAX_GPARAMS = 32
 VARIANT_FLAG_GENERIC = 0x100
@@ -99,6 +99,7 @@ class Stats(C.Structure):
         ("inum", C.c_int), ("nall", C.c_int), ("max_neigh_list", C.c_int), ("max_neigh_cut", C.c_int),
         ("avg_neigh_cut", C.c_double), ("sum_triplets", C.c_double), ("kernel_launches", C.c_longlong),
         ("last_force_kernel_ms", C.c_float), ("force_kernel_ms_total", C.c_double), ("force_kernel_samples", C.c_int),
+        ("overflow_pass_atoms", C.c_longlong), ("tile_capacity", C.c_int), ("stage_cycles", C.c_double * 8),
     ]
 
 
@@ -115,6 +116,11 @@ PROTOTYPES = {
     "anna_b200_init": (C.c_int, [C.POINTER(AnnaParams), C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),
     "annp_b200_init": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),
     "annp_b200_clear": (None, [C.c_void_p]),
+    "annp_b200_neigh_build_host": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double]),
+    "annp_b200_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "annp_b200_host_unregister": (C.c_int, [C.c_void_p]),
+    "annp_b200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "annp_b200_host_free": (None, [C.c_void_p]),
     "annp_b200_bytes": (C.c_double, [C.c_void_p]),
     "annp_b200_last_error": (C.c_char_p, [C.c_void_p]),
     "annp_b200_neigh": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_int_p, c_int_p, C.POINTER(c_int_p)]),

@@ -14,9 +14,9 @@
 
 // ---- kernels' host entry points (annp_force.cu / annp_aux.cu / annp_neigh.cu)
 size_t annp_force_smem_bytes(const DevParams &hp, int capacity);
-bool annp_force_supported(int npsf, int ntsf);
-cudaError_t annp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream, int *blocks_out);
-cudaError_t annp_bp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream);
+bool annp_force_kernel_shape(int npsf, int ntsf, int variant, int *npsf_k, int *ntsf_k);
+cudaError_t annp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream, int max_blocks);
+cudaError_t annp_bp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream, int max_blocks);
 int annp_bp_layout(const DevParams &hp);
 void aux_pack_xq(const double *x, const int *type, double4 *xq, int nall, cudaStream_t s);
 void aux_build_reverse(const int *nbr, long long total, int nall, long long *rev_off, int *rev_pos, int *cnt, int *tmp,
@@ -95,6 +95,25 @@ __global__ void k_count_cut(const DevParams *prm, const double4 *__restrict__ xq
   if (lane == 0) atomicMax(maxn, best);
 }
 
+// a caller-supplied list must only name atoms 0..nall-1: bad[0] counts ilist entries and masked neighbour indices outside
+// that range, bad[1] rows whose offsets decrease (the force kernels index xq / facc / centre_of with these numbers)
+__global__ void k_validate_list(const int *__restrict__ ilist, const long long *__restrict__ row_off, const int *__restrict__ nbr,
+                                int inum, long long total, int nall, int *__restrict__ bad) {
+  const long long stride = (long long) gridDim.x * blockDim.x;
+  int nb = 0, nr = 0;
+  for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int j = nbr[t] & ANNP_NEIGHMASK;
+    nb += (j >= nall);
+  }
+  for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < inum; t += stride) {
+    const int i = ilist[t];
+    nb += (i < 0 || i >= nall);
+    nr += (row_off[t + 1] < row_off[t]);
+  }
+  if (nb) atomicAdd(bad, nb);
+  if (nr) atomicAdd(bad + 1, nr);
+}
+
 }    // namespace
 
 struct annp_b200_handle_s {
@@ -111,7 +130,9 @@ struct annp_b200_handle_s {
   // device neighbour build scratch
   DevBuf d_cell_of, d_cell_cnt, d_cell_off, d_cell_atoms, d_row_cnt, d_small;
   // per-step
-  DevBuf d_xq, d_fpair, d_facc, d_fself, d_vir_c, d_vpair, d_partial, d_counters, d_engvir, d_Gdbg, d_dEdbg;
+  DevBuf d_xq, d_fpair, d_facc, d_fself, d_vir_c, d_vpair, d_partial, d_counters, d_engvir, d_Gdbg, d_dEdbg, d_ovf_list;
+  // descriptor shape of the potential; hp.npsf / hp.ntsf / hp.nsf are the (possibly padded) shape of the kernel instantiation
+  int npsf_file = 0, ntsf_file = 0;
   // how neighbour forces reach f: 1 = fixed-point integer atomics into d_facc (default),
   // 0 = per-entry pair forces (d_fpair) summed by an ordered gather over the reverse map (annp_b200_set_scatter)
   int scatter_fixed = 0;
@@ -125,6 +146,9 @@ struct annp_b200_handle_s {
   DevBuf d_goff, d_glist, d_ke_partial;
   int capacity = 0;
   bool need_calibrate = true;
+  bool types_valid = false;           // host mode: d_type holds the types of the current atoms (annp_b200_compute with type == NULL)
+  void *pin_list = nullptr;           // pinned staging of the flattened host neighbour list (annp_b200_neigh)
+  size_t pin_list_cap = 0;
   bool timing = false;
   bool debug_desc = false;
   static constexpr int kEvRing = 256;
@@ -211,7 +235,11 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
   else CK(h->d_fpair.reserve(sizeof(double4) * (size_t) std::max<long long>(h->total, 1)));
   if (!fixed || want_vatom) { int rc = ensure_reverse(h, s); if (rc) return rc; }
   CK(h->d_fself.reserve(sizeof(double4) * (size_t) std::max(inum, 1)));
-  CK(h->d_counters.reserve(sizeof(DevCounters)));
+  CK(h->d_ovf_list.reserve(sizeof(int) * (size_t) std::max(inum, 1)));
+  if (!h->d_counters.p) {
+    CK(h->d_counters.reserve(sizeof(DevCounters)));
+    CK(cudaMemsetAsync(h->d_counters.p, 0, sizeof(DevCounters), s));     // the sticky flags start clear
+  }
   CK(h->d_partial.reserve(sizeof(double) * 7 * (size_t) aux_reduce_blocks(inum)));
   if (want_vir || want_vatom) CK(h->d_vir_c.reserve(sizeof(double) * 6 * (size_t) std::max(inum, 1)));
   if (want_vatom) CK(h->d_vpair.reserve(sizeof(double) * 6 * (size_t) std::max<long long>(h->total, 1)));
@@ -242,10 +270,9 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
       h->capacity = std::max(h->capacity, round_capacity(std::min(h->max_row, ANNP_B200_MAX_NEIGH)));
     }
     h->need_calibrate = false;
-    CK(cudaMemsetAsync(h->d_counters.p, 0, sizeof(DevCounters), s));
   }
 
-  // reset the scheduler and statistics, keep the sticky overflow flag
+  // reset the schedulers and the per-step statistics; the sticky flags (overflow, bad_force) stay until they are reported
   CK(cudaMemsetAsync(h->d_counters.p, 0, offsetof(DevCounters, overflow), s));
 
   ForceArgs a;
@@ -265,15 +292,36 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
   a.cnt = h->d_counters.as<DevCounters>();
   a.inum = inum;
   a.capacity = h->capacity;
+  a.work_list = nullptr;
+  a.work_count = nullptr;
+  a.work_ctr = &a.cnt->work;
+  a.ovf_list = h->d_ovf_list.as<int>();
+  // Overflow pass: atoms whose in-cutoff neighbours outgrew the first-pass tile (they moved inside the skin since the tile
+  // was sized) are redone with a tile of the list's longest row - a list row cannot overflow that.  The pass is a second
+  // launch of the same kernel over the device-side list the first pass wrote (one block per SM; it exits at once when the
+  // list is empty), so a device-resident step is complete without a host round trip.
+  const int cap_full = round_capacity(std::min(std::max(h->max_row, 1), ANNP_B200_MAX_NEIGH));
+  const bool need_pass2 = cap_full > h->capacity;
 
   if (inum > 0) {
     const bool timed = h->timing && h->ev_count < annp_b200_handle_s::kEvRing;
     if (timed) { CK(cudaEventRecord(h->ev0[h->ev_count], s)); }
-    cudaError_t e = (h->hp.variant == ANNP_B200_VARIANT_NI) ? annp_bp_force_launch(a, h->hp, h->num_sms, s)
-                                                            : annp_force_launch(a, h->hp, h->num_sms, s, nullptr);
+    const bool ni = h->hp.variant == ANNP_B200_VARIANT_NI;
+    cudaError_t e = ni ? annp_bp_force_launch(a, h->hp, h->num_sms, s, 0) : annp_force_launch(a, h->hp, h->num_sms, s, 0);
     if (e != cudaSuccess) return cuda_fail(h, e, "annp_force_launch");
     if (timed) { CK(cudaEventRecord(h->ev1[h->ev_count], s)); h->ev_count++; }
     h->launches += 1;
+    if (need_pass2) {
+      ForceArgs b = a;
+      b.capacity = cap_full;
+      b.work_list = a.ovf_list;
+      b.work_count = &a.cnt->ovf_count;
+      b.work_ctr = &a.cnt->work2;
+      b.ovf_list = nullptr;                     // beyond the largest tile: sticky overflow flag, reported as an error
+      e = ni ? annp_bp_force_launch(b, h->hp, h->num_sms, s, h->num_sms) : annp_force_launch(b, h->hp, h->num_sms, s, h->num_sms);
+      if (e != cudaSuccess) return cuda_fail(h, e, "annp_force_launch (overflow pass)");
+      h->launches += 1;
+    }
   }
   if (d_f && fixed) {
     aux_finish_force(h->d_facc.as<long long>(), h->d_fself.as<double4>(), h->d_centre_of.as<int>(), d_f, nall, s);
@@ -299,7 +347,12 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
 
 int fetch_counters(annp_b200_handle h, cudaStream_t s) {
   CK(cudaMemcpyAsync(&h->last_cnt, h->d_counters.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, s));
+  // the sticky part is handed to the caller (who reports it) and starts clear again
+  CK(cudaMemsetAsync((char *) h->d_counters.p + offsetof(DevCounters, overflow), 0, sizeof(DevCounters) - offsetof(DevCounters, overflow), s));
   CK(cudaStreamSynchronize(s));
+  // atoms took the overflow pass: size the first-pass tile for them from now on
+  if (h->last_cnt.ovf_total > 0 && h->last_cnt.max_neigh + (h->last_cnt.max_neigh & 1) > h->capacity)
+    h->capacity = round_capacity(std::min(h->last_cnt.max_neigh + 12, ANNP_B200_MAX_NEIGH));
   for (int k = 0; k < h->ev_count; k++) {
     float ms = 0.f;
     cudaEventSynchronize(h->ev1[k]);
@@ -396,6 +449,26 @@ static bool valid_shape(int ntypes, int nelements, int ntl, int nnod, int nsf, i
            npsf < 1 || ntsf < 1);
 }
 
+// The kernel shape (npsf_k, ntsf_k) may be larger than the potential's (npsf, ntsf): descriptor component n < npsf keeps
+// its place, angular component t moves to npsf_k + t, and the added components get zero scale / zero first-layer weights,
+// so they contribute exact zeros to the energy and to every derivative.
+static int padded_index(int n, int npsf, int npsf_k) { return n < npsf ? n : npsf_k + (n - npsf); }
+
+static std::vector<double> pad_weights(const double *w, int nelements, int nl, int nnod, int nout, int nsf, int npsf, int npsf_k, int nsf_k) {
+  std::vector<double> out;
+  const double *src = w;
+  for (int e = 0; e < nelements; e++)
+    for (int l = 0; l < nl; l++) {
+      const int nr = (l == nl - 1) ? nout : nnod, nc = (l == 0) ? nsf : nnod, nck = (l == 0) ? nsf_k : nnod;
+      const size_t base = out.size();
+      out.resize(base + (size_t) nr * nck, 0.0);
+      for (int r = 0; r < nr; r++)
+        for (int c = 0; c < nc; c++) out[base + (size_t) r * nck + (l == 0 ? padded_index(c, npsf, npsf_k) : c)] = src[(size_t) r * nc + c];
+      src += (size_t) nr * nc;
+    }
+  return out;
+}
+
 // weights, biases, (Chebyshev variants) the monomial conversion matrix, then the parameter block itself
 static int upload_params(annp_b200_handle h, const double *weights, const double *bias, bool chebyshev, char *err, int errlen) {
   DevParams &hp = h->hp;
@@ -445,22 +518,25 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
     set_err(err, errlen, "parameter block outside the supported range");
     return ANNP_B200_EINVAL;
   }
-  if (!ni && !annp_force_supported(p->npsf, p->ntsf)) {
-    set_err(err, errlen, "no kernel instantiation for this (npsf, ntsf); add it to pick_kernel in annp_force.cu");
+  int npsf_k = p->npsf, ntsf_k = p->ntsf;
+  if (!ni && !annp_force_kernel_shape(p->npsf, p->ntsf, variant, &npsf_k, &ntsf_k)) {
+    set_err(err, errlen, "Chebyshev descriptor beyond the kernel's range: npsf <= 16 and ntsf <= 24 (the monomial form of the angular polynomial is well conditioned up to degree 23)");
     return ANNP_B200_EINVAL;
   }
+  const int nsf_k = npsf_k + ntsf_k;
   if (!p->sfnor_scal || !p->sfnor_avg || !p->cutsq || !p->map || !p->weights || !p->bias) { set_err(err, errlen, "null parameter array"); return ANNP_B200_EINVAL; }
   if (ni && (!p->sym_coerad || !p->sym_coeang)) { set_err(err, errlen, "the Ni variant needs sym_coerad / sym_coeang"); return ANNP_B200_EINVAL; }
 
   annp_b200_handle h = nullptr;
   int rc = open_handle(device, &h, err, errlen);
   if (rc) return rc;
-  rc = fill_network(h, p->ntypes, p->nelements, p->ntl, p->nnod, 1, p->nsf, p->npsf, p->ntsf, p->flagact, p->cutsq, p->map, p->cut, err, errlen);
+  rc = fill_network(h, p->ntypes, p->nelements, p->ntl, p->nnod, 1, nsf_k, npsf_k, ntsf_k, p->flagact, p->cutsq, p->map, p->cut, err, errlen);
   if (rc) { annp_b200_clear(h); return rc; }
+  h->npsf_file = p->npsf; h->ntsf_file = p->ntsf;
   DevParams &hp = h->hp;
   hp.variant = variant;
   hp.e_scale = p->e_scale; hp.e_shift = p->e_shift; hp.e_atom = p->e_atom;
-  for (int n = 0; n < p->nsf; n++) { hp.sf_scale[n] = p->sfnor_scal[n]; hp.sf_avg[n] = p->sfnor_avg[n]; }
+  for (int n = 0; n < p->nsf; n++) { const int k = padded_index(n, p->npsf, npsf_k); hp.sf_scale[k] = p->sfnor_scal[n]; hp.sf_avg[k] = p->sfnor_avg[n]; }
   if (ni) {
     for (int m = 0; m < p->npsf; m++) hp.rad_eta[m] = p->sym_coerad[m * 3 + 0];
     hp.rad_rc = p->sym_coerad[2];                          // Rc of the first row, as the reference (ni/src/pair_annp.cpp:690)
@@ -471,7 +547,12 @@ int annp_b200_init(const annp_b200_params *p, int device, int nall_hint, int max
     hp.bp_layout = (p->variant & ANNP_B200_VARIANT_FLAG_GENERIC) ? 0 : annp_bp_layout(hp);
     if (hp.bp_layout == 1 && (p->variant & ANNP_B200_VARIANT_FLAG_NOPAIR)) hp.bp_layout = 2;
   }
-  rc = upload_params(h, p->weights, p->bias, !ni, err, errlen);
+  if (nsf_k != p->nsf) {
+    const std::vector<double> wk = pad_weights(p->weights, p->nelements, p->ntl - 1, p->nnod, 1, p->nsf, p->npsf, npsf_k, nsf_k);
+    rc = upload_params(h, wk.data(), p->bias, !ni, err, errlen);
+  } else {
+    rc = upload_params(h, p->weights, p->bias, !ni, err, errlen);
+  }
   if (rc) { annp_b200_clear(h); return rc; }
   h->scatter_fixed = 1;
   *out = h;
@@ -488,22 +569,30 @@ int anna_b200_init(const anna_b200_params *p, int device, annp_b200_handle *out,
     set_err(err, errlen, "parameter block outside the supported range (ANNA-ADP needs nout = 2 and >= 17 global parameters)");
     return ANNP_B200_EINVAL;
   }
-  if (!annp_force_supported(p->npsf, p->ntsf)) {
-    set_err(err, errlen, "no kernel instantiation for this (npsf, ntsf); add it to pick_kernel in annp_force.cu");
+  int npsf_k = p->npsf, ntsf_k = p->ntsf;
+  if (!annp_force_kernel_shape(p->npsf, p->ntsf, ANNP_B200_VARIANT_ANNA_ADP, &npsf_k, &ntsf_k)) {
+    set_err(err, errlen, "Chebyshev descriptor beyond the kernel's range: npsf <= 16 and ntsf <= 24");
     return ANNP_B200_EINVAL;
   }
+  const int nsf_k = npsf_k + ntsf_k;
   if (!p->cutsq || !p->map || !p->weights || !p->bias || !p->gparams) { set_err(err, errlen, "null parameter array"); return ANNP_B200_EINVAL; }
   annp_b200_handle h = nullptr;
   int rc = open_handle(device, &h, err, errlen);
   if (rc) return rc;
-  rc = fill_network(h, p->ntypes, p->nelements, p->ntl, p->nnod, p->nout, p->nsf, p->npsf, p->ntsf, p->flagact, p->cutsq, p->map, p->cut, err, errlen);
+  rc = fill_network(h, p->ntypes, p->nelements, p->ntl, p->nnod, p->nout, nsf_k, npsf_k, ntsf_k, p->flagact, p->cutsq, p->map, p->cut, err, errlen);
   if (rc) { annp_b200_clear(h); return rc; }
+  h->npsf_file = p->npsf; h->ntsf_file = p->ntsf;
   DevParams &hp = h->hp;
   hp.variant = ANNP_B200_VARIANT_ANNA_ADP;
   hp.e_base = p->e_base;
   for (int k = 0; k < 17; k++) hp.gparams[k] = p->gparams[k];
-  for (int n = 0; n < p->nsf; n++) { hp.sf_scale[n] = 1.0; hp.sf_avg[n] = 0.0; }   // raw descriptor (pair_anna_adp.cpp:124-166)
-  rc = upload_params(h, p->weights, p->bias, true, err, errlen);   // the forward pass needs the block-basis conversion matrix
+  for (int n = 0; n < p->nsf; n++) { const int k = padded_index(n, p->npsf, npsf_k); hp.sf_scale[k] = 1.0; hp.sf_avg[k] = 0.0; }   // raw descriptor (pair_anna_adp.cpp:124-166)
+  // the forward pass needs the block-basis conversion matrix
+  if (nsf_k != p->nsf) {
+    const std::vector<double> wk = pad_weights(p->weights, p->nelements, p->ntl - 1, p->nnod, p->nout, p->nsf, p->npsf, npsf_k, nsf_k);
+    rc = upload_params(h, wk.data(), p->bias, true, err, errlen);
+  } else
+    rc = upload_params(h, p->weights, p->bias, true, err, errlen);
   if (rc) { annp_b200_clear(h); return rc; }
   h->scatter_fixed = 1;
   *out = h;
@@ -520,6 +609,8 @@ void annp_b200_clear(annp_b200_handle h) {
                     &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,
                     &h->d_eatom, &h->d_vatom, &h->d_goff, &h->d_glist, &h->d_ke_partial};
   for (DevBuf *b : bufs) b->release();
+  h->d_ovf_list.release();
+  if (h->pin_list) cudaFreeHost(h->pin_list);
   for (int k = 0; k < annp_b200_handle_s::kEvRing; k++) {
     if (h->ev0[k]) cudaEventDestroy(h->ev0[k]);
     if (h->ev1[k]) cudaEventDestroy(h->ev1[k]);
@@ -537,7 +628,7 @@ double annp_b200_bytes(annp_b200_handle h) {
                           &h->d_eatom, &h->d_vatom, &h->d_goff, &h->d_glist, &h->d_ke_partial};
   double b = 0.0;
   for (const DevBuf *d : bufs) b += (double) d->cap;
-  return b;
+  return b + (double) h->d_ovf_list.cap;
 }
 
 const char *annp_b200_last_error(annp_b200_handle h) { return h ? h->err.c_str() : "null handle"; }
@@ -563,69 +654,121 @@ int annp_b200_neigh_csr(annp_b200_handle h, int inum, int nall, const int *ilist
     const long long zero = 0;
     CK(cudaMemcpyAsync(h->d_row_off.p, &zero, sizeof(long long), cudaMemcpyHostToDevice, s));
   }
+  int bad[2] = {0, 0};
+  if (inum > 0) {
+    if (offsets[0] != 0) return fail(h, ANNP_B200_EINVAL, "neighbour list offsets must start at 0");
+    CK(h->d_small.reserve(64));
+    CK(cudaMemsetAsync(h->d_small.p, 0, 2 * sizeof(int), s));
+    k_validate_list<<<std::min<long long>(148 * 8, (std::max<long long>(total, inum) + 255) / 256), 256, 0, s>>>(
+        h->d_ilist.as<int>(), h->d_row_off.as<long long>(), h->d_nbr.as<int>(), inum, total, nall, h->d_small.as<int>());
+    h->launches += 1;
+    CK(cudaMemcpyAsync(bad, h->d_small.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
   int rc = finish_list(h, s);
   if (rc) return rc;
   CK(cudaStreamSynchronize(s));
+  if (bad[0] || bad[1]) {
+    h->have_list = false;
+    return fail(h, ANNP_B200_EINVAL, bad[1] ? "neighbour list offsets decrease" : "neighbour list names atoms outside 0..nall-1");
+  }
   return ANNP_B200_OK;
 }
 
 int annp_b200_neigh(annp_b200_handle h, int inum, int nall, const int *ilist, const int *numneigh, const int *const *firstneigh) {
   if (!h) return ANNP_B200_EINVAL;
   if (inum < 0 || (inum > 0 && (!ilist || !numneigh || !firstneigh))) return fail(h, ANNP_B200_EINVAL, "bad neighbour list arguments");
-  // flatten LAMMPS' paged rows (NeighList::firstneigh) into CSR in ilist order
+  CK(cudaSetDevice(h->device));
+  // flatten LAMMPS' paged rows (NeighList::firstneigh) into CSR in ilist order, straight into a page-locked staging buffer
+  // (kept across calls) so the upload is one DMA at PCIe speed instead of a pageable copy
   std::vector<int64_t> off((size_t) inum + 1, 0);
-  for (int ii = 0; ii < inum; ii++) off[ii + 1] = off[ii] + numneigh[ilist[ii]];
-  std::vector<int> flat((size_t) off[inum]);
   for (int ii = 0; ii < inum; ii++) {
     const int i = ilist[ii];
-    if (numneigh[i] > 0) memcpy(flat.data() + off[ii], firstneigh[i], sizeof(int) * (size_t) numneigh[i]);
+    if (i < 0 || i >= nall || numneigh[i] < 0) return fail(h, ANNP_B200_EINVAL, "neighbour list names atoms outside 0..nall-1");
+    off[ii + 1] = off[ii] + numneigh[i];
   }
-  return annp_b200_neigh_csr(h, inum, nall, ilist, off.data(), flat.data());
+  const size_t bytes = sizeof(int) * (size_t) std::max<int64_t>(off[inum], 1);
+  if (bytes > h->pin_list_cap) {
+    if (h->pin_list) cudaFreeHost(h->pin_list);
+    h->pin_list = nullptr; h->pin_list_cap = 0;
+    const size_t want = bytes + bytes / 8;
+    if (cudaHostAlloc(&h->pin_list, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(h, ANNP_B200_ENOMEM, "cannot page-lock the neighbour list staging buffer"); }
+    h->pin_list_cap = want;
+  }
+  int *flat = (int *) h->pin_list;
+  for (int ii = 0; ii < inum; ii++) {
+    const int i = ilist[ii];
+    if (numneigh[i] > 0) memcpy(flat + off[ii], firstneigh[i], sizeof(int) * (size_t) numneigh[i]);
+  }
+  return annp_b200_neigh_csr(h, inum, nall, ilist, off.data(), flat);
+}
+
+int annp_b200_host_register(void *ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return ANNP_B200_EINVAL;
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+  if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return ANNP_B200_OK; }
+  if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorMemoryAllocation ? ANNP_B200_ENOMEM : ANNP_B200_ECUDA; }
+  return ANNP_B200_OK;
+}
+
+int annp_b200_host_unregister(void *ptr) {
+  if (!ptr) return ANNP_B200_OK;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorHostMemoryNotRegistered ? ANNP_B200_OK : ANNP_B200_ECUDA; }
+  return ANNP_B200_OK;
+}
+
+void *annp_b200_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void annp_b200_host_free(void *ptr) {
+  if (ptr && cudaFreeHost(ptr) != cudaSuccess) cudaGetLastError();
 }
 
 int annp_b200_compute(annp_b200_handle h, int nlocal, int nghost, const double *x, const int *type, int eflag, int vflag,
                       double *f, double *eng, double *eatom, double *virial6, double *vatom) {
   if (!h) return ANNP_B200_EINVAL;
   const int nall = nlocal + nghost;
-  if (nall < 0 || (nall > 0 && (!x || !type))) return fail(h, ANNP_B200_EINVAL, "bad position/type arguments");
+  if (nall < 0 || (nall > 0 && !x)) return fail(h, ANNP_B200_EINVAL, "bad position/type arguments");
+  if (nall > 0 && !type && !(h->types_valid && h->d_type.cap >= sizeof(int) * (size_t) nall))
+    return fail(h, ANNP_B200_ESTATE, "type == NULL needs an earlier call that passed the types of these atoms");
   CK(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
   CK(h->d_x.reserve(sizeof(double) * 3 * (size_t) std::max(nall, 1)));
-  CK(h->d_type.reserve(sizeof(int) * (size_t) std::max(nall, 1)));
+  if (type || !h->d_type.p) { h->types_valid = false; CK(h->d_type.reserve(sizeof(int) * (size_t) std::max(nall, 1))); }
   CK(h->d_f.reserve(sizeof(double) * 3 * (size_t) std::max(nall, 1)));
   CK(h->d_engvir.reserve(sizeof(double) * 8));
   if (eatom) CK(h->d_eatom.reserve(sizeof(double) * (size_t) std::max(nall, 1)));
   if (vatom) CK(h->d_vatom.reserve(sizeof(double) * 6 * (size_t) std::max(nall, 1)));
   if (nall > 0) {
+    // x / type / f may be pageable (the copy is then staged by the driver) or page-locked (annp_b200_host_register /
+    // annp_b200_host_alloc: direct DMA at PCIe speed)
     CK(cudaMemcpyAsync(h->d_x.p, x, sizeof(double) * 3 * (size_t) nall, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(h->d_type.p, type, sizeof(int) * (size_t) nall, cudaMemcpyHostToDevice, s));
+    if (type) {
+      CK(cudaMemcpyAsync(h->d_type.p, type, sizeof(int) * (size_t) nall, cudaMemcpyHostToDevice, s));
+      h->types_valid = true;
+    }
   }
   if (eatom) CK(cudaMemsetAsync(h->d_eatom.p, 0, sizeof(double) * (size_t) std::max(nall, 1), s));
   const bool want_ev = (eng && eflag) || (virial6 && vflag);
-  for (int attempt = 0; attempt < 4; attempt++) {
-    int rc = step_device(h, nlocal, nghost, h->d_x.as<double>(), h->d_type.as<int>(), eflag, (virial6 || vatom) ? (vflag ? vflag : 1) : 0,
-                         f ? h->d_f.as<double>() : nullptr, eatom ? h->d_eatom.as<double>() : nullptr,
-                         want_ev ? h->d_engvir.as<double>() : nullptr, vatom ? h->d_vatom.as<double>() : nullptr, s, true);
-    if (rc) return rc;
-    rc = fetch_counters(h, s);
-    if (rc) return rc;
-    if (h->last_cnt.bad_force) {
-      CK(cudaMemsetAsync(h->d_counters.p, 0, sizeof(DevCounters), s));
-      return fail(h, ANNP_B200_EOVERFLOW, "a pair force is NaN or beyond 2^18 eV/A (fixed-point force accumulation): the configuration is unphysical");
-    }
-    if (!h->last_cnt.overflow) break;
-    // a neighbour tile overflowed (atoms moved inside the skin): grow and redo the step
-    if (h->last_cnt.max_neigh > ANNP_B200_MAX_NEIGH) return fail(h, ANNP_B200_EOVERFLOW, "an atom has more in-cutoff neighbours than ANNP_B200_MAX_NEIGH");
-    h->capacity = round_capacity(std::min(h->last_cnt.max_neigh + 12, ANNP_B200_MAX_NEIGH));
-    CK(cudaMemsetAsync(h->d_counters.p, 0, sizeof(DevCounters), s));
-    if (attempt == 3) return fail(h, ANNP_B200_EOVERFLOW, "neighbour tile kept overflowing");
-  }
+  int rc = step_device(h, nlocal, nghost, h->d_x.as<double>(), h->d_type.as<int>(), eflag, (virial6 || vatom) ? (vflag ? vflag : 1) : 0,
+                       f ? h->d_f.as<double>() : nullptr, eatom ? h->d_eatom.as<double>() : nullptr,
+                       want_ev ? h->d_engvir.as<double>() : nullptr, vatom ? h->d_vatom.as<double>() : nullptr, s, true);
+  if (rc) return rc;
+  // results are queued behind the kernels; ONE synchronisation at the end covers them and the counters
   double ev[7] = {0, 0, 0, 0, 0, 0, 0};
   if (want_ev) CK(cudaMemcpyAsync(ev, h->d_engvir.p, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
   if (f && nall > 0) CK(cudaMemcpyAsync(f, h->d_f.p, sizeof(double) * 3 * (size_t) nall, cudaMemcpyDeviceToHost, s));
   if (eatom && nall > 0) CK(cudaMemcpyAsync(eatom, h->d_eatom.p, sizeof(double) * (size_t) nall, cudaMemcpyDeviceToHost, s));
   if (vatom && nall > 0) CK(cudaMemcpyAsync(vatom, h->d_vatom.p, sizeof(double) * 6 * (size_t) nall, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  rc = fetch_counters(h, s);          // synchronises the stream
+  if (rc) return rc;
+  if (h->last_cnt.bad_force)
+    return fail(h, ANNP_B200_EOVERFLOW, "a pair force is NaN or beyond 2^18 eV/A (fixed-point force accumulation): the configuration is unphysical");
+  if (h->last_cnt.overflow)
+    return fail(h, ANNP_B200_EOVERFLOW, "an atom has more in-cutoff neighbours than ANNP_B200_MAX_NEIGH");
   if (eng && eflag) *eng = ev[0];
   if (virial6 && vflag) for (int k = 0; k < 6; k++) virial6[k] = ev[1 + k];
   return ANNP_B200_OK;
@@ -682,6 +825,19 @@ int annp_b200_neigh_build(annp_b200_handle h, int nlocal, int nall, const double
     CK(cudaStreamSynchronize(s));
   }
   return finish_list(h, s);
+}
+
+int annp_b200_neigh_build_host(annp_b200_handle h, int nlocal, int nall, const double *x, const double *bbox_lo, const double *bbox_hi,
+                               double cutneigh) {
+  if (!h) return ANNP_B200_EINVAL;
+  if (nlocal < 0 || nall < nlocal || (nall > 0 && !x)) return fail(h, ANNP_B200_EINVAL, "bad neigh_build arguments");
+  CK(cudaSetDevice(h->device));
+  CK(h->d_x.reserve(sizeof(double) * 3 * (size_t) std::max(nall, 1)));
+  if (nall > 0) CK(cudaMemcpyAsync(h->d_x.p, x, sizeof(double) * 3 * (size_t) nall, cudaMemcpyHostToDevice, h->stream));
+  const int rc = annp_b200_neigh_build(h, nlocal, nall, h->d_x.as<double>(), bbox_lo, bbox_hi, cutneigh, h->stream);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return ANNP_B200_OK;
 }
 
 int annp_b200_set_halo(annp_b200_handle h, int nlocal, int nsend, const int *d_index, const double *d_shift, void *stream) {
@@ -761,8 +917,12 @@ int annp_b200_get_stats(annp_b200_handle h, annp_b200_stats *out) {
   out->last_force_kernel_ms = h->last_force_ms;
   out->force_kernel_ms_total = h->force_ms_total;
   out->force_kernel_samples = h->force_samples;
-  if (h->last_cnt.overflow) return fail(h, ANNP_B200_EOVERFLOW, "neighbour tile overflow in a device-mode step: results of that step are invalid");
-  if (h->last_cnt.bad_force) return fail(h, ANNP_B200_EOVERFLOW, "a pair force was NaN or beyond 2^18 eV/A in a device-mode step (fixed-point force accumulation)");
+  out->overflow_pass_atoms = (long long) h->last_cnt.ovf_total;
+  out->tile_capacity = h->capacity;
+  for (int k = 0; k < 8; k++) out->stage_cycles[k] = (double) h->last_cnt.stage_clk[k];
+  // sticky flags of every device-mode step since the last call (fetch_counters cleared them on the device)
+  if (h->last_cnt.overflow) return fail(h, ANNP_B200_EOVERFLOW, "an atom had more in-cutoff neighbours than ANNP_B200_MAX_NEIGH in a device-mode step since the last check: results from that step on are invalid");
+  if (h->last_cnt.bad_force) return fail(h, ANNP_B200_EOVERFLOW, "a pair force was NaN or beyond 2^18 eV/A in a device-mode step since the last check (fixed-point force accumulation)");
   return ANNP_B200_OK;
 }
 
@@ -787,9 +947,15 @@ int annp_b200_debug_descriptors(annp_b200_handle h, double *G, double *dE_dG) {
   if (!h->d_Gdbg.p) return fail(h, ANNP_B200_ESTATE, "no compute since the capture was armed");
   CK(cudaSetDevice(h->device));
   CK(cudaDeviceSynchronize());
-  const size_t n = sizeof(double) * (size_t) h->hp.nsf * h->inum;
-  if (G) CK(cudaMemcpy(G, h->d_Gdbg.p, n, cudaMemcpyDeviceToHost));
-  if (dE_dG) CK(cudaMemcpy(dE_dG, h->d_dEdbg.p, n, cudaMemcpyDeviceToHost));
+  const int nsf_k = h->hp.nsf, nsf = h->npsf_file + h->ntsf_file;
+  std::vector<double> tmp((size_t) nsf_k * std::max(h->inum, 1));
+  for (int pass = 0; pass < 2; pass++) {
+    double *dst = pass ? dE_dG : G;
+    if (!dst) continue;
+    CK(cudaMemcpy(tmp.data(), pass ? h->d_dEdbg.p : h->d_Gdbg.p, sizeof(double) * (size_t) nsf_k * h->inum, cudaMemcpyDeviceToHost));
+    for (int ii = 0; ii < h->inum; ii++)
+      for (int n = 0; n < nsf; n++) dst[(size_t) ii * nsf + n] = tmp[(size_t) ii * nsf_k + padded_index(n, h->npsf_file, h->hp.npsf)];
+  }
   return ANNP_B200_OK;
 }
 

@@ -43,12 +43,21 @@ struct DevParams {
 
 // counters written by the force kernel (one block of 8 x 8 bytes)
 struct DevCounters {
-  unsigned long long work;        // dynamic atom scheduler
+  // ---- reset before every step (everything in front of `overflow`)
+  unsigned long long work;        // dynamic atom scheduler, first pass
+  unsigned long long work2;       // dynamic atom scheduler, overflow pass
   unsigned long long sum_neigh;   // sum of in-cutoff neighbours
   unsigned long long sum_trip;    // sum of N(N-1)/2
   int max_neigh;                  // max in-cutoff neighbours
-  int overflow;                   // an atom exceeded the smem capacity
+  int ovf_count;                  // atoms of this step whose in-cutoff neighbours did not fit the first-pass tile: they are
+                                  // listed in ForceArgs::ovf_list and redone by the overflow pass with a tile of the list's
+                                  // longest row, so the step's results are complete whatever the atoms did inside the skin
+  // ---- sticky: only annp_b200_get_stats / the host-mode compute read AND clear them, reporting the failure
+  int overflow;                   // an atom has more in-cutoff neighbours than the LARGEST tile (ANNP_B200_MAX_NEIGH)
   int bad_force;                  // a neighbour force left the fixed-point range (|F| >= 2^ANNP_FIX_LIMIT_BITS eV/A) or is NaN
+  unsigned long long ovf_total;   // atoms redone by the overflow pass since the counters were last read (statistics)
+  unsigned long long stage_clk[8];// ANNP_STAGE_CLOCKS builds: SM cycles per stage summed over warps (filter, radial, forward,
+                                  // reduce+MLP, backward, force, scheduler)
 };
 
 struct ForceArgs {
@@ -68,7 +77,26 @@ struct ForceArgs {
   DevCounters *cnt;
   int inum;
   int capacity;               // smem neighbour slots per warp
+  // work items: first pass = all inum centres (work_list null); overflow pass = the ovf_count centres listed by the first
+  // pass (work_list = that list, work_count = its device-side length)
+  const int *work_list;
+  const int *work_count;
+  unsigned long long *work_ctr;
+  int *ovf_list;              // [inum] first pass: centres that need the overflow pass; null in the overflow pass itself
 };
+
+// number of work items of this launch and the centre index of item `item`
+__device__ __forceinline__ unsigned long long annp_work_items(const ForceArgs &a) {
+  return a.work_count ? (unsigned long long) *a.work_count : (unsigned long long) a.inum;
+}
+__device__ __forceinline__ int annp_work_centre(const ForceArgs &a, unsigned long long item) {
+  return a.work_list ? a.work_list[item] : (int) item;
+}
+// the in-cutoff neighbours of centre ii do not fit this launch's tile (call from one lane)
+__device__ __forceinline__ void annp_note_overflow(const ForceArgs &a, int ii) {
+  if (a.ovf_list) a.ovf_list[atomicAdd(&a.cnt->ovf_count, 1)] = ii;
+  else atomicExch(&a.cnt->overflow, 1);
+}
 
 // activation tables of the reference copies: Fe pair_annp.cpp:709-739, Ni ni/src/pair_annp.cpp:786-807,
 // ANNA-ADP pair_anna_adp.cpp:694-718 (3 and 4 = 1.7 tanh(0.3 x); only h is used there)

@@ -122,12 +122,14 @@ __global__ void __launch_bounds__(kWarps * 32) annp_bp_force_kernel(const ForceA
   const double Rc_rad = P.rad_rc, Rc_ang = P.ang_rc;
   const double Rc_max = fmax(Rc_rad, Rc_ang);
 
+  const unsigned long long nwork = annp_work_items(a);
+  if (a.work_list && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.cnt->ovf_total, nwork);   // overflow pass: statistics
   for (;;) {
     unsigned long long item = 0;
-    if (lane == 0) item = atomicAdd(&a.cnt->work, 1ull);
+    if (lane == 0) item = atomicAdd(a.work_ctr, 1ull);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= (unsigned long long) a.inum) break;
-    const int ii = (int) item;
+    if (item >= nwork) break;
+    const int ii = annp_work_centre(a, item);
     const int i = a.ilist[ii];
     const double4 xi = a.xq[i];
     const int ti = (int) xi.w;
@@ -166,13 +168,13 @@ __global__ void __launch_bounds__(kWarps * 32) annp_bp_force_kernel(const ForceA
       }
       N += __popc(mask);
     }
-    if (lane == 0) {
+    if (lane == 0 && !a.work_list) {
       atomicMax(&a.cnt->max_neigh, N);
       atomicAdd(&a.cnt->sum_neigh, (unsigned long long) N);
       atomicAdd(&a.cnt->sum_trip, (unsigned long long) N * (unsigned long long) (N > 0 ? N - 1 : 0) / 2ull);
     }
     if (N > C) {
-      if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
+      if (lane == 0) { annp_note_overflow(a, ii); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
       if (!a.facc) for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
       __syncwarp();
       continue;
@@ -367,12 +369,14 @@ __global__ void __launch_bounds__(kWarps * 32, 3) annp_bp_fast_kernel(const Forc
 #pragma unroll
   for (int e = 0; e < NE; e++) eta[e] = P.ang_eta[e * NZ * 2];
 
+  const unsigned long long nwork = annp_work_items(a);
+  if (a.work_list && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.cnt->ovf_total, nwork);   // overflow pass: statistics
   for (;;) {
     unsigned long long item = 0;
-    if (lane == 0) item = atomicAdd(&a.cnt->work, 1ull);
+    if (lane == 0) item = atomicAdd(a.work_ctr, 1ull);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= (unsigned long long) a.inum) break;
-    const int ii = (int) item;
+    if (item >= nwork) break;
+    const int ii = annp_work_centre(a, item);
     const int i = a.ilist[ii];
     const double4 xi = a.xq[i];
     const int ti = (int) xi.w;
@@ -415,13 +419,13 @@ __global__ void __launch_bounds__(kWarps * 32, 3) annp_bp_fast_kernel(const Forc
       }
       N += __popc(mask);
     }
-    if (lane == 0) {
+    if (lane == 0 && !a.work_list) {
       atomicMax(&a.cnt->max_neigh, N);
       atomicAdd(&a.cnt->sum_neigh, (unsigned long long) N);
       atomicAdd(&a.cnt->sum_trip, (unsigned long long) N * (unsigned long long) (N > 0 ? N - 1 : 0) / 2ull);
     }
     if (N > C) {
-      if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
+      if (lane == 0) { annp_note_overflow(a, ii); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
       if (!a.facc) for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
       __syncwarp();
       continue;
@@ -646,12 +650,14 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
 #pragma unroll
   for (int e = 0; e < NE; e++) eta[e] = P.ang_eta[e * NZ * 2];
 
+  const unsigned long long nwork = annp_work_items(a);
+  if (a.work_list && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&a.cnt->ovf_total, nwork);   // overflow pass: statistics
   for (;;) {
     unsigned long long item = 0;
-    if (lane == 0) item = atomicAdd(&a.cnt->work, 1ull);
+    if (lane == 0) item = atomicAdd(a.work_ctr, 1ull);
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= (unsigned long long) a.inum) break;
-    const int ii = (int) item;
+    if (item >= nwork) break;
+    const int ii = annp_work_centre(a, item);
     const int i = a.ilist[ii];
     const double4 xi = a.xq[i];
     const int ti = (int) xi.w;
@@ -702,13 +708,13 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
         N += __popc(mask);
       }
     }
-    if (lane == 0) {
+    if (lane == 0 && !a.work_list) {
       atomicMax(&a.cnt->max_neigh, N);
       atomicAdd(&a.cnt->sum_neigh, (unsigned long long) N);
       atomicAdd(&a.cnt->sum_trip, (unsigned long long) N * (unsigned long long) (N > 0 ? N - 1 : 0) / 2ull);
     }
     if (N > C) {
-      if (lane == 0) { atomicExch(&a.cnt->overflow, 1); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
+      if (lane == 0) { annp_note_overflow(a, ii); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
       if (!a.facc) for (int q = lane; q < L; q += 32) a.fpair[p0 + q] = make_double4(0.0, 0.0, 0.0, 0.0);
       __syncwarp();
       continue;
@@ -952,7 +958,7 @@ static size_t annp_bp_pair_smem_bytes(const DevParams &hp) {
   return blk + kWarps * per_warp;
 }
 
-cudaError_t annp_bp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream) {
+cudaError_t annp_bp_force_launch(const ForceArgs &args, const DevParams &hp, int num_sms, cudaStream_t stream, int max_blocks) {
   // product-structured table: pair-compaction kernel while the tile fits one warp, lane-per-neighbour kernel beyond
   const bool pairk = hp.bp_layout == 1 && args.capacity <= 32;
   const size_t smem = pairk ? annp_bp_pair_smem_bytes(hp) : annp_bp_smem_bytes(hp, args.capacity);
@@ -966,6 +972,7 @@ cudaError_t annp_bp_force_launch(const ForceArgs &args, const DevParams &hp, int
   long long want = ((long long) args.inum + kWarps - 1) / kWarps;
   long long blocks = (long long) per_sm * num_sms;
   if (blocks > want) blocks = want;
+  if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;       // overflow pass: item count known on the device only
   if (blocks < 1) blocks = 1;
   kern<<<(unsigned) blocks, kWarps * 32, smem, stream>>>(args);
   return cudaGetLastError();

@@ -35,8 +35,7 @@ using namespace LAMMPS_NS;
 
 /* ---------------------------------------------------------------------- */
 
-PairANNAADPB200::PairANNAADPB200(LAMMPS *lmp) :
-    PairANNA_ADP(lmp), handle(nullptr), nmax_buf(0), fbuf(nullptr), ebuf(nullptr), vbuf(nullptr)
+PairANNAADPB200::PairANNAADPB200(LAMMPS *lmp) : PairANNA_ADP(lmp), handle(nullptr), fstage(nullptr), device_neigh(0)
 {
   respa_enable = 0;
   suffix_flag |= Suffix::GPU;
@@ -48,35 +47,16 @@ PairANNAADPB200::PairANNAADPB200(LAMMPS *lmp) :
 
 PairANNAADPB200::~PairANNAADPB200()
 {
+  hb.clear();
   annp_b200_clear(handle);
   handle = nullptr;
-  free(fbuf);
-  free(ebuf);
-  free(vbuf);
 }
 
 /* ---------------------------------------------------------------------- */
 
 double PairANNAADPB200::memory_usage()
 {
-  double bytes = Pair::memory_usage();
-  bytes += (double) nmax_buf * 10 * sizeof(double);
-  return bytes + annp_b200_bytes(handle);
-}
-
-/* ---------------------------------------------------------------------- */
-
-void PairANNAADPB200::grow_buffers(int nall, int want_e, int want_v)
-{
-  if (nall > nmax_buf) {
-    nmax_buf = nall + nall / 8 + 16;
-    free(fbuf); free(ebuf); free(vbuf);
-    fbuf = (double *) malloc(sizeof(double) * 3 * (size_t) nmax_buf);
-    ebuf = vbuf = nullptr;
-  }
-  if (want_e && !ebuf) ebuf = (double *) malloc(sizeof(double) * (size_t) nmax_buf);
-  if (want_v && !vbuf) vbuf = (double *) malloc(sizeof(double) * 6 * (size_t) nmax_buf);
-  if (!fbuf || (want_e && !ebuf) || (want_v && !vbuf)) error->one(FLERR, "Out of host memory in pair anna_adp/gpu");
+  return Pair::memory_usage() + hb.bytes() + annp_b200_bytes(handle);
 }
 
 /* ----------------------------------------------------------------------
@@ -87,39 +67,56 @@ void PairANNAADPB200::compute(int eflag, int vflag)
 {
   ev_init(eflag, vflag);
   const int nlocal = atom->nlocal, nghost = atom->nghost, nall = nlocal + nghost;
-  double **f = atom->f;
+  const bool rebuilt = neighbor->ago == 0;
   int rc;
 
-  if (neighbor->ago == 0) {
-    rc = annp_b200_neigh(handle, list->inum, nall, list->ilist, list->numneigh, list->firstneigh);
+  if (nall > 0) hb.x.track(atom->x[0], sizeof(double) * 3 * (size_t) atom->nmax);
+
+  if (rebuilt) {
+    if (device_neigh) {
+      double lo[3], hi[3];
+      ANNP_B200_NS::bounds_of(nall > 0 ? atom->x[0] : nullptr, nall, lo, hi);
+      rc = annp_b200_neigh_build_host(handle, nlocal, nall, nall > 0 ? atom->x[0] : nullptr, lo, hi, cutmax + neighbor->skin);
+    } else {
+      rc = annp_b200_neigh(handle, list->inum, nall, list->ilist, list->numneigh, list->firstneigh);
+    }
     if (rc == ANNP_B200_ENOMEM) error->one(FLERR, "Insufficient memory on accelerator");
     if (rc) error->one(FLERR, std::string("anna_adp/gpu: ") + annp_b200_last_error(handle));
   }
   if (nall == 0) return;
-  grow_buffers(nall, eflag_atom, vflag_atom);
+
+  // only pair style of a newton-on run: the device writes straight into LAMMPS' page-locked force array (see
+  // annp_b200_host.h); otherwise the forces are staged (pair hybrid: added; newton off: folded by the style itself)
+  const bool direct = force->pair == this && force->newton_pair;
+  double *f0 = atom->f[0];
+  double *fdst = f0;
+  if (direct) hb.f.track(f0, sizeof(double) * 3 * (size_t) atom->nmax);
+  else fdst = hb.fbuf.reserve(3 * (size_t) nall);
+  double *ebuf = eflag_atom ? hb.ebuf.reserve((size_t) nall) : nullptr;
+  double *vbuf = vflag_atom ? hb.vbuf.reserve(6 * (size_t) nall) : nullptr;
+  if (!fdst || (eflag_atom && !ebuf) || (vflag_atom && !vbuf)) error->one(FLERR, "Out of host memory in pair anna_adp/gpu");
 
   double eng = 0.0, vir[6] = {0, 0, 0, 0, 0, 0};
   const int want_pair_virial = vflag_global && !vflag_fdotr;
-  rc = annp_b200_compute(handle, nlocal, nghost, atom->x[0], atom->type, eflag_either, vflag_either || vflag_fdotr,
-                         fbuf, eflag_global ? &eng : nullptr, eflag_atom ? ebuf : nullptr,
-                         want_pair_virial ? vir : nullptr, vflag_atom ? vbuf : nullptr);
+  rc = annp_b200_compute(handle, nlocal, nghost, atom->x[0], rebuilt ? atom->type : nullptr, eflag_either, vflag_either || vflag_fdotr,
+                         fdst, eflag_global ? &eng : nullptr, ebuf, want_pair_virial ? vir : nullptr, vbuf);
   if (rc == ANNP_B200_ENOMEM) error->one(FLERR, "Insufficient memory on accelerator");
   if (rc) error->one(FLERR, std::string("anna_adp/gpu: ") + annp_b200_last_error(handle));
 
-  double *f0 = f[0];
   if (force->newton_pair) {
     // local and ghost rows: LAMMPS' reverse_comm carries the ghost part home
-    for (int i = 0; i < 3 * nall; i++) f0[i] += fbuf[i];
+    if (!direct) ANNP_B200_NS::add_into(f0, fdst, 3 * (size_t) nall);
   } else {
     // `newton off`: LAMMPS will not reverse-communicate forces, so the style does it for its own ghost rows
+    fstage = fdst;
     comm->reverse_comm(this);
-    for (int i = 0; i < 3 * nlocal; i++) f0[i] += fbuf[i];
+    fstage = nullptr;
+    ANNP_B200_NS::add_into(f0, fdst, 3 * (size_t) nlocal);
   }
   if (eflag_global) eng_vdwl += eng;
-  if (eflag_atom) for (int i = 0; i < nall; i++) eatom[i] += ebuf[i];
+  if (eflag_atom) ANNP_B200_NS::add_into(eatom, ebuf, (size_t) nall);
   if (want_pair_virial) for (int k = 0; k < 6; k++) virial[k] += vir[k];
-  if (vflag_atom)
-    for (int i = 0; i < nall; i++) for (int k = 0; k < 6; k++) vatom[i][k] += vbuf[6 * (size_t) i + k];
+  if (vflag_atom) ANNP_B200_NS::add_into(vatom[0], vbuf, 6 * (size_t) nall);
 
   if (vflag_fdotr) virial_fdotr_compute();
 }
@@ -132,9 +129,9 @@ int PairANNAADPB200::pack_reverse_comm(int n, int first, double *buf)
 {
   int m = 0;
   for (int i = first; i < first + n; i++) {
-    buf[m++] = fbuf[3 * (size_t) i];
-    buf[m++] = fbuf[3 * (size_t) i + 1];
-    buf[m++] = fbuf[3 * (size_t) i + 2];
+    buf[m++] = fstage[3 * (size_t) i];
+    buf[m++] = fstage[3 * (size_t) i + 1];
+    buf[m++] = fstage[3 * (size_t) i + 2];
   }
   return m;
 }
@@ -144,9 +141,9 @@ void PairANNAADPB200::unpack_reverse_comm(int n, int *list, double *buf)
   int m = 0;
   for (int i = 0; i < n; i++) {
     const int j = list[i];
-    fbuf[3 * (size_t) j] += buf[m++];
-    fbuf[3 * (size_t) j + 1] += buf[m++];
-    fbuf[3 * (size_t) j + 2] += buf[m++];
+    fstage[3 * (size_t) j] += buf[m++];
+    fstage[3 * (size_t) j + 1] += buf[m++];
+    fstage[3 * (size_t) j + 2] += buf[m++];
   }
 }
 
@@ -199,9 +196,12 @@ void PairANNAADPB200::init_style()
   const int ndev = annp_b200_device_count();
   char msg[512] = "";
   const int device = ndev > 0 ? comm->me % ndev : 0;      // one rank per GPU
-  const int rc = anna_b200_init(&P, device, &handle, msg, (int) sizeof(msg));
-  if (rc == ANNP_B200_ENOMEM) error->all(FLERR, "Insufficient memory on accelerator");
-  if (rc != 0) error->all(FLERR, std::string("anna_adp/gpu initialisation failed: ") + msg);
+  int rc = anna_b200_init(&P, device, &handle, msg, (int) sizeof(msg));
+  // reduce the code over all ranks before aborting, as GPU_EXTRA::check_flag does for the reference (codes are <= 0)
+  int rc_all = rc;
+  MPI_Allreduce(&rc, &rc_all, 1, MPI_INT, MPI_MIN, world);
+  if (rc_all == ANNP_B200_ENOMEM) error->all(FLERR, "Insufficient memory on accelerator");
+  if (rc_all != 0) error->all(FLERR, std::string("anna_adp/gpu initialisation failed") + (rc != 0 ? std::string(": ") + msg : std::string(" on another rank")));
   // The input deck keeps the reference's zero-argument pair_style line; ANNP_B200_SCATTER=gather selects the ordered
   // FP64 gather instead of the default fixed-point force accumulation (include/annp_b200.h: annp_b200_set_scatter)
   if (const char *sc = getenv("ANNP_B200_SCATTER")) {
@@ -209,5 +209,6 @@ void PairANNAADPB200::init_style()
     if (mode < 0 || annp_b200_set_scatter(handle, mode) != 0) error->all(FLERR, "ANNP_B200_SCATTER must be 'fixed' or 'gather'");
   }
 
-  neighbor->add_request(this, NeighConst::REQ_FULL);
+  device_neigh = ANNP_B200_NS::device_neigh_requested() ? 1 : 0;      // `package gpu N neigh yes` of the reference
+  if (!device_neigh) neighbor->add_request(this, NeighConst::REQ_FULL);
 }

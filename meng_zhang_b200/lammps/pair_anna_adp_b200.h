@@ -25,6 +25,7 @@ PairStyle(anna_adp/gpu, PairANNAADPB200);
 #define LMP_PAIR_ANNA_ADP_B200_H
 
 #include "pair_anna_adp.h"      // the reference's CPU style: file parsing, coeff(), init_one()
+#include "annp_b200_host.h"
 
 struct annp_b200_handle_s;
 
@@ -42,9 +43,9 @@ class PairANNAADPB200 : public PairANNA_ADP {
 
  protected:
   annp_b200_handle_s *handle;
-  int nmax_buf;
-  double *fbuf, *ebuf, *vbuf;     // host staging: forces / per-atom energy / per-atom virial
-  void grow_buffers(int nall, int want_e, int want_v);
+  ANNP_B200_NS::HostBuffers hb;   // page-locked views of atom->x / atom->f and the style's own staging arrays
+  double *fstage;                 // forces of the current compute() while the style's own reverse_comm runs (newton off)
+  int device_neigh;               // ANNP_B200_NEIGH=device: neighbour list built on the GPU
 };
 
 }    // namespace LAMMPS_NS

@@ -84,7 +84,7 @@ template <class P> typename std::enable_if<is_ni_copy<P>::value>::type fill_desc
 
 /* ---------------------------------------------------------------------- */
 
-PairANNPB200::PairANNPB200(LAMMPS *lmp) : PairANNP(lmp), handle(nullptr), nmax_buf(0), fbuf(nullptr), ebuf(nullptr), vbuf(nullptr)
+PairANNPB200::PairANNPB200(LAMMPS *lmp) : PairANNP(lmp), handle(nullptr), device_neigh(0)
 {
   respa_enable = 0;
   suffix_flag |= Suffix::GPU;
@@ -94,35 +94,16 @@ PairANNPB200::PairANNPB200(LAMMPS *lmp) : PairANNP(lmp), handle(nullptr), nmax_b
 
 PairANNPB200::~PairANNPB200()
 {
+  hb.clear();
   annp_b200_clear(handle);
   handle = nullptr;
-  free(fbuf);
-  free(ebuf);
-  free(vbuf);
 }
 
 /* ---------------------------------------------------------------------- */
 
 double PairANNPB200::memory_usage()
 {
-  double bytes = Pair::memory_usage();
-  bytes += (double) nmax_buf * 10 * sizeof(double);
-  return bytes + annp_b200_bytes(handle);
-}
-
-/* ---------------------------------------------------------------------- */
-
-void PairANNPB200::grow_buffers(int nall, int want_e, int want_v)
-{
-  if (nall > nmax_buf) {
-    nmax_buf = nall + nall / 8 + 16;
-    free(fbuf); free(ebuf); free(vbuf);
-    fbuf = (double *) malloc(sizeof(double) * 3 * (size_t) nmax_buf);
-    ebuf = vbuf = nullptr;
-  }
-  if (want_e && !ebuf) ebuf = (double *) malloc(sizeof(double) * (size_t) nmax_buf);
-  if (want_v && !vbuf) vbuf = (double *) malloc(sizeof(double) * 6 * (size_t) nmax_buf);
-  if (!fbuf || (want_e && !ebuf) || (want_v && !vbuf)) error->one(FLERR, "Out of host memory in pair annp/gpu");
+  return Pair::memory_usage() + hb.bytes() + annp_b200_bytes(handle);
 }
 
 /* ----------------------------------------------------------------------
@@ -133,33 +114,50 @@ void PairANNPB200::compute(int eflag, int vflag)
 {
   ev_init(eflag, vflag);
   const int nlocal = atom->nlocal, nghost = atom->nghost, nall = nlocal + nghost;
-  double **f = atom->f;
+  const bool rebuilt = neighbor->ago == 0;
   int rc;
 
-  if (neighbor->ago == 0) {    // reset_nbors of the reference: hand the full list to the device
-    rc = annp_b200_neigh(handle, list->inum, nall, list->ilist, list->numneigh, list->firstneigh);
+  // LAMMPS' position array, page-locked in place (re-registered when Memory::grow moved it)
+  if (nall > 0) hb.x.track(atom->x[0], sizeof(double) * 3 * (size_t) atom->nmax);
+
+  if (rebuilt) {
+    if (device_neigh) {     // annp_gpu_compute_n of the reference: the list is built on the device from the positions
+      double lo[3], hi[3];
+      ANNP_B200_NS::bounds_of(nall > 0 ? atom->x[0] : nullptr, nall, lo, hi);
+      rc = annp_b200_neigh_build_host(handle, nlocal, nall, nall > 0 ? atom->x[0] : nullptr, lo, hi, cutmax + neighbor->skin);
+    } else {                // reset_nbors of the reference: hand LAMMPS' full list to the device
+      rc = annp_b200_neigh(handle, list->inum, nall, list->ilist, list->numneigh, list->firstneigh);
+    }
     if (rc == ANNP_B200_ENOMEM) error->one(FLERR, "Insufficient memory on accelerator");
     if (rc) error->one(FLERR, std::string("annp/gpu: ") + annp_b200_last_error(handle));
   }
   if (nall == 0) return;
-  grow_buffers(nall, eflag_atom, vflag_atom);
+
+  // Only pair style of the run: LAMMPS has zeroed f, the device writes the forces straight into the page-locked array
+  // (the reference assigns f too, lal_annp.cpp:345-347).  As a sub-style of pair hybrid / overlay they are staged and added.
+  const bool sole = force->pair == this;
+  double *f0 = atom->f[0];
+  double *fdst = f0;
+  if (sole) hb.f.track(f0, sizeof(double) * 3 * (size_t) atom->nmax);
+  else fdst = hb.fbuf.reserve(3 * (size_t) nall);
+  double *ebuf = eflag_atom ? hb.ebuf.reserve((size_t) nall) : nullptr;
+  double *vbuf = vflag_atom ? hb.vbuf.reserve(6 * (size_t) nall) : nullptr;
+  if (!fdst || (eflag_atom && !ebuf) || (vflag_atom && !vbuf)) error->one(FLERR, "Out of host memory in pair annp/gpu");
 
   double eng = 0.0, vir[6] = {0, 0, 0, 0, 0, 0};
   const int want_pair_virial = vflag_global && !vflag_fdotr;
-  rc = annp_b200_compute(handle, nlocal, nghost, atom->x[0], atom->type, eflag_either, vflag_either || vflag_fdotr,
-                         fbuf, eflag_global ? &eng : nullptr, eflag_atom ? ebuf : nullptr,
-                         want_pair_virial ? vir : nullptr, vflag_atom ? vbuf : nullptr);
+  // types travel with the list: atoms keep their slots (and types) until the next re-neighbouring
+  rc = annp_b200_compute(handle, nlocal, nghost, atom->x[0], rebuilt ? atom->type : nullptr, eflag_either, vflag_either || vflag_fdotr,
+                         fdst, eflag_global ? &eng : nullptr, ebuf, want_pair_virial ? vir : nullptr, vbuf);
   if (rc == ANNP_B200_ENOMEM) error->one(FLERR, "Insufficient memory on accelerator");
   if (rc) error->one(FLERR, std::string("annp/gpu: ") + annp_b200_last_error(handle));
 
   // local and ghost rows: LAMMPS' reverse_comm carries the ghost part home (newton_pair on)
-  double *f0 = f[0];
-  for (int i = 0; i < 3 * nall; i++) f0[i] += fbuf[i];
+  if (!sole) ANNP_B200_NS::add_into(f0, fdst, 3 * (size_t) nall);
   if (eflag_global) eng_vdwl += eng;
-  if (eflag_atom) for (int i = 0; i < nall; i++) eatom[i] += ebuf[i];
+  if (eflag_atom) ANNP_B200_NS::add_into(eatom, ebuf, (size_t) nall);
   if (want_pair_virial) for (int k = 0; k < 6; k++) virial[k] += vir[k];
-  if (vflag_atom)
-    for (int i = 0; i < nall; i++) for (int k = 0; k < 6; k++) vatom[i][k] += vbuf[6 * (size_t) i + k];
+  if (vflag_atom) ANNP_B200_NS::add_into(vatom[0], vbuf, 6 * (size_t) nall);
 
   if (vflag_fdotr) virial_fdotr_compute();
 }
@@ -227,10 +225,14 @@ void PairANNPB200::init_style()
   const int ndev = annp_b200_device_count();
   char msg[512] = "";
   const int device = ndev > 0 ? comm->me % ndev : 0;      // one rank per GPU
-  const int rc = annp_b200_init(&P, device, atom->nlocal + atom->nghost, 0, &handle, msg, (int) sizeof(msg));
-  // the reference funnels init codes through GPU_EXTRA::check_flag, which aborts all ranks (line 235)
-  if (rc == ANNP_B200_ENOMEM) error->all(FLERR, "Insufficient memory on accelerator");
-  if (rc != 0) error->all(FLERR, std::string("annp/gpu initialisation failed: ") + msg);
+  int rc = annp_b200_init(&P, device, atom->nlocal + atom->nghost, 0, &handle, msg, (int) sizeof(msg));
+  // the reference funnels init codes through GPU_EXTRA::check_flag, which reduces them over all ranks before aborting
+  // (line 235): a failure on one rank (out of memory, no device) must stop every rank, or the others hang in the next
+  // collective.  Codes are <= 0, so the minimum over the ranks is the worst one.
+  int rc_all = rc;
+  MPI_Allreduce(&rc, &rc_all, 1, MPI_INT, MPI_MIN, world);
+  if (rc_all == ANNP_B200_ENOMEM) error->all(FLERR, "Insufficient memory on accelerator");
+  if (rc_all != 0) error->all(FLERR, std::string("annp/gpu initialisation failed") + (rc != 0 ? std::string(": ") + msg : std::string(" on another rank")));
   // The input deck keeps the reference's zero-argument pair_style line; ANNP_B200_SCATTER=gather selects the ordered
   // FP64 gather instead of the default fixed-point force accumulation (include/annp_b200.h: annp_b200_set_scatter)
   if (const char *sc = getenv("ANNP_B200_SCATTER")) {
@@ -238,5 +240,8 @@ void PairANNPB200::init_style()
     if (mode < 0 || annp_b200_set_scatter(handle, mode) != 0) error->all(FLERR, "ANNP_B200_SCATTER must be 'fixed' or 'gather'");
   }
 
-  neighbor->add_request(this, NeighConst::REQ_FULL);
+  // ANNP_B200_NEIGH=device: the reference's GPU_NEIGH mode (`package gpu N neigh yes`, annp_gpu_compute_n): the library
+  // builds the full list on the device from the positions, LAMMPS builds none for this style
+  device_neigh = ANNP_B200_NS::device_neigh_requested() ? 1 : 0;
+  if (!device_neigh) neighbor->add_request(this, NeighConst::REQ_FULL);
 }

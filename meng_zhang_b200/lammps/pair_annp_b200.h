@@ -9,6 +9,10 @@
 
        pair_style  annp/gpu
        pair_coeff  * * fe_annp_potential_2.ann Fe
+
+   Environment (the deck keeps the reference's zero-argument pair_style line):
+       ANNP_B200_NEIGH=device    build the neighbour list on the GPU (the reference's `package gpu N neigh yes`)
+       ANNP_B200_SCATTER=gather  ordered FP64 gather instead of the fixed-point force accumulation
 ------------------------------------------------------------------------- */
 
 #ifdef PAIR_CLASS
@@ -21,6 +25,7 @@ PairStyle(annp/gpu, PairANNPB200);
 #define LMP_PAIR_ANNP_B200_H
 
 #include "pair_annp.h"      // the reference's CPU style: file parsing, coeff(), init_one()
+#include "annp_b200_host.h"
 
 struct annp_b200_handle_s;
 
@@ -36,9 +41,8 @@ class PairANNPB200 : public PairANNP {
 
  protected:
   annp_b200_handle_s *handle;
-  int nmax_buf;
-  double *fbuf, *ebuf, *vbuf;     // host staging: forces / per-atom energy / per-atom virial
-  void grow_buffers(int nall, int want_e, int want_v);
+  ANNP_B200_NS::HostBuffers hb;   // page-locked views of atom->x / atom->f and the style's own staging arrays
+  int device_neigh;               // ANNP_B200_NEIGH=device: neighbour list built on the GPU (`package gpu ... neigh yes`)
 };
 
 }    // namespace LAMMPS_NS

@@ -55,11 +55,12 @@ def read_output(path):
         f = np.frombuffer(fp.read(nall * 24), dtype="<f8").reshape(nall, 3).copy()
         eatom = np.frombuffer(fp.read(nall * 8), dtype="<f8").copy() if has_e else None
         vatom = np.frombuffer(fp.read(nall * 48), dtype="<f8").reshape(nall, 6).copy() if has_v else None
+        per_call = np.frombuffer(fp.read(ncalls * 8), dtype="<f8").copy()
     return {"eng_vdwl": eng, "virial": virial, "f": f, "eatom": eatom, "vatom": vatom,
-            "seconds": secs, "ncalls": ncalls}
+            "seconds": secs, "ncalls": ncalls, "per_call_seconds": per_call}
 
 
-def run_reference(kind, cfg, potential_file, elements, eflag=3, vflag=2, ncalls=1, timeout=3600, newton=None):
+def run_reference(kind, cfg, potential_file, elements, eflag=3, vflag=2, ncalls=1, timeout=3600, newton=None, env_extra=None):
     """One `Pair::compute(eflag, vflag)` of the reference style `kind` on cfg.
 
     Returns eng_vdwl, virial[6], f[nall,3] (ghost forces NOT folded), eatom, vatom, seconds."""
@@ -72,6 +73,7 @@ def run_reference(kind, cfg, potential_file, elements, eflag=3, vflag=2, ncalls=
         env = dict(os.environ)
         if newton is not None:
             env["ANNP_DRIVER_NEWTON"] = str(int(newton))      # the deck's `newton on|off`
+        env.update(env_extra or {})
         p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
         if p.returncode != 0:
             raise RuntimeError(f"reference driver failed ({p.returncode}): {p.stderr[-2000:]}")

@@ -10,6 +10,7 @@ Needs /root/reference and the binaries of `make -C oracle` (oracle/_ref/ref_*). 
                                    (eng_vdwl, eatom, f, virial by pair tally and by f.r, vatom)
   tests/golden/ni_potential.json, anna_potential.json, annp_ni_*.npz, anna_adp_*.npz
                                    the same for the Ni copy of the style (ref_annp_ni) and for ANNA-ADP (ref_anna_adp)
+  tests/golden/annp_general_*.npz  synthetic potentials (other shapes, activations, element counts) + the reference's answers
   tests/golden/fe_st.npz           the 152 880-atom slab of `performance test.zip` + its logged thermo values
 The GPU box has no /root/reference: tests read only these files.
 """
@@ -194,6 +195,44 @@ def dump_kind(kind, prefix, potfile, cases_fn):
               f"fmax {np.abs(cfg.fold(r1['f'])).max():.6e} ({r1['seconds']:.1f} s)")
 
 
+def dump_general():
+    """Potentials the shipped files do not exercise, through the UNMODIFIED reference: activations 1, 2, 3
+    and a non-linear output layer, a five-layer network, descriptor shapes (8,20), (6,11), (12,22), (16,24), two element
+    blocks.  The potential files are written by pair.write_potential from the synthetic numbers of util.general_potential;
+    the golden file stores those numbers next to the reference's answers."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+    from meng_zhang_b200.pair import write_potential
+    x, box = L.bcc(4, 4, 4)
+    for name in util.GENERAL_CASES:
+        pot, elems = util.general_potential(name)
+        if len(elems) > 1:
+            types = np.random.default_rng(11).integers(1, len(elems) + 1, size=len(x)).astype(np.int32)
+            cfg = L.build_config(L.perturb(x, 0.05, 4711), box, pot.cut, types=types, shuffle_rows=5)
+        else:
+            cfg = L.build_config(L.perturb(x, 0.05, 4711), box, pot.cut, shuffle_rows=5)
+        with tempfile.TemporaryDirectory() as td:
+            pf = os.path.join(td, f"{name}.ann")
+            write_potential(pf, pot, comment=f"synthetic potential {name}")
+            r1 = run_reference("annp_fe", cfg, pf, elems, eflag=3, vflag=1 + 4)
+            r2 = run_reference("annp_fe", cfg, pf, elems, eflag=3, vflag=2)
+        assert np.array_equal(r1["f"], r2["f"])
+        np.savez_compressed(
+            os.path.join(OUT, f"annp_general_{name}.npz"),
+            nlocal=cfg.nlocal, nghost=cfg.nghost, x=cfg.x, type=cfg.type, ghost_owner=cfg.ghost_owner,
+            ilist=cfg.ilist, numneigh=cfg.numneigh, neigh=cfg.neigh, box=cfg.box, elements=np.array(elems),
+            eng_vdwl=r1["eng_vdwl"], eatom=r1["eatom"], f=r1["f"], virial_pair=r1["virial"], virial_fdotr=r2["virial"],
+            vatom=r1["vatom"], ref_seconds=r1["seconds"],
+            pot_nelements=pot.nelements, pot_ntl=pot.ntl, pot_nnod=pot.nnod, pot_npsf=pot.npsf, pot_ntsf=pot.ntsf,
+            pot_flagact=np.array(pot.flagact), pot_cut=pot.cut, pot_e_scale=pot.e_scale, pot_e_shift=pot.e_shift, pot_e_atom=pot.e_atom,
+            pot_elements=np.array(pot.elements), pot_sfnor_cov=pot.sfnor_cov, pot_sfnor_avg=pot.sfnor_avg,
+            pot_weight_all=pot.weight_all, pot_bias_all=pot.bias_all)
+        ec = r1["eatom"][: cfg.nlocal] - pot.e_shift - pot.e_atom
+        print(f"general {name}: E/atom {r1['eng_vdwl'] / cfg.nlocal:.10f} cohesive part {ec.min():.4f}..{ec.max():.4f} "
+              f"fmax {np.abs(cfg.fold(r1['f'])).max():.6e} ({r1['seconds']:.1f} s)")
+
+
 def dump_fe_st_log():
     """Thermo table of the reference's own published run (numbers only): 1 001 rows of
     Step Temp PotEng KinEng Lx Ly Lz Press Volume Pxx Pyy Pzz from log_relaxing_{new,old}.lammps, plus the minimiser
@@ -262,6 +301,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "log":
         dump_fe_st_log()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "general":     # only the round-2 additions
+        dump_general()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "structures":
         dump_structures()
         sys.exit(0)
@@ -278,3 +320,4 @@ if __name__ == "__main__":
     dump_fe_st_log()
     dump_fe_st()
     dump_cases()
+    dump_general()

@@ -282,3 +282,185 @@ def test_lammps_pair_style_through_the_shim_driver(name, fe_pot_file):
     finally:
         del os.environ["ANNP_B200_SCATTER"]
     assert np.abs(gathered - ref["f"]).max() <= TOL_F and np.abs(gathered - fixed).max() <= 2e-11
+
+
+@pytest.mark.parametrize("name", ["bcc4_perturbed", "cluster_ragged"])
+def test_lammps_pair_style_host_paths(name, fe_pot_file):
+    """The paths of PairANNPB200::compute the single-call test above does not reach:
+    * repeated calls on one list (neighbor->ago > 0: no list upload, types not re-sent, LAMMPS' x / f page-locked in place
+      and the forces written straight into atom->f);
+    * the sub-style situation of pair hybrid (Force::pair is another object): forces staged and ADDED;
+    * ANNP_B200_NEIGH=device, the reference's `package gpu N neigh yes` (annp_gpu_compute_n): the list is built on the
+      device from the positions, in a different order than LAMMPS' - same atoms in every row, so the same forces to
+      rounding."""
+    from oracle import run_ref
+    if not run_ref.available("plugin_annp_b200"):
+        pytest.skip("plugin binary not built")
+    cfg, elems, ref = util.load_case(name)
+    one = run_ref.run_reference("plugin_annp_b200", cfg, fe_pot_file, elems, eflag=3, vflag=1 + 4)
+    many = run_ref.run_reference("plugin_annp_b200", cfg, fe_pot_file, elems, eflag=3, vflag=1 + 4, ncalls=4)
+    assert len(many["per_call_seconds"]) == 4
+    assert np.array_equal(many["f"], one["f"]) and np.array_equal(many["eatom"], one["eatom"]) and np.array_equal(many["vatom"], one["vatom"])
+    hyb = run_ref.run_reference("plugin_annp_b200", cfg, fe_pot_file, elems, eflag=3, vflag=1 + 4, ncalls=3, env_extra={"ANNP_DRIVER_HYBRID": "1"})
+    assert np.array_equal(hyb["f"], one["f"]) and hyb["eng_vdwl"] == one["eng_vdwl"]
+    dev = run_ref.run_reference("plugin_annp_b200", cfg, fe_pot_file, elems, eflag=3, vflag=1 + 4, ncalls=2, env_extra={"ANNP_B200_NEIGH": "device"})
+    assert np.abs(dev["eatom"] - ref["eatom"]).max() <= TOL_E
+    assert np.abs(dev["f"] - ref["f"]).max() <= TOL_F
+    assert np.abs(dev["virial"] - ref["virial_pair"]).max() <= TOL_V
+    assert np.abs(dev["vatom"] - ref["vatom"]).max() <= TOL_F
+
+
+def test_bad_neighbour_lists_are_refused(fe_pot_file):
+    """A list that names atoms outside 0..nall-1 or whose offsets decrease must fail with EINVAL instead of indexing
+    device memory out of bounds."""
+    cfg, elems, ref = util.load_case("bcc4_perturbed")
+    pair = make_pair(fe_pot_file, elems)
+    Lb = capi.lib()
+    ilist = np.ascontiguousarray(cfg.ilist, dtype=np.int32)
+    off = np.ascontiguousarray(cfg.offsets, dtype=np.int64)
+    neigh = np.ascontiguousarray(cfg.neigh, dtype=np.int32)
+    ip = lambda a: a.ctypes.data_as(capi.c_int_p)
+    call = lambda il, o, ng, nall=cfg.nall: Lb.annp_b200_neigh_csr(pair.handle, len(il), nall, ip(il), o.ctypes.data_as(capi.c_int64_p), ip(ng))
+    bad = neigh.copy(); bad[17] = cfg.nall + 3
+    assert call(ilist, off, bad) == capi.EINVAL
+    assert call(ilist, off, neigh, nall=cfg.nall - 1) == capi.EINVAL        # nall disagrees with the list
+    bad_il = ilist.copy(); bad_il[5] = -1
+    assert call(bad_il, off, neigh) == capi.EINVAL
+    bad_off = off.copy(); bad_off[3] = bad_off[2] - 1
+    assert call(ilist, bad_off, neigh) == capi.EINVAL
+    with pytest.raises(capi.AnnpError):                                      # no list is installed after a refusal
+        pair.compute(1, 0, cfg, ago=1)
+    assert call(ilist, off, neigh) == 0
+    assert np.abs(pair.compute(1, 0, cfg, ago=1) - ref["f"]).max() <= TOL_F
+    pair.clear()
+
+
+# ---- general potentials (SURVEY 8f row 4): everything the reference's CPU style reads must run on the GPU ------------------
+
+@pytest.mark.parametrize("name", util.GENERAL_CASES)
+def test_general_potentials_against_the_reference(name, tmp_path):
+    """Descriptor shapes without an exact kernel instantiation (zero-padded onto <8,24> / <16,24>, the latter with the
+    two-round descriptor reduction), the exact <8,20> instantiation, activations 1, 2 (with the reference's sign), 3, a
+    non-linear output layer, five layers, 32 nodes per layer, and a two-element file: golden answers of the UNMODIFIED
+    reference (tests/golden/make_golden.py general)."""
+    from meng_zhang_b200.pair import write_potential
+    cfg, elems, ref, pot = util.load_general_case(name)
+    pf = str(tmp_path / f"{name}.ann")
+    write_potential(pf, pot)
+    pair = make_pair(pf, elems)
+    f = pair.compute(3, 1 + 4, cfg, ago=0)
+    assert np.abs(pair.eatom - ref["eatom"]).max() <= TOL_E
+    assert np.abs(f - ref["f"]).max() <= TOL_F
+    assert np.abs(pair.virial - ref["virial_pair"]).max() <= TOL_V
+    assert np.abs(pair.vatom - ref["vatom"]).max() <= TOL_F
+    assert np.array_equal(f, pair.compute(0, 0, cfg, ago=1))
+    # the ordered-gather scatter runs the other template instantiation of the same shape
+    pair.set_scatter(capi.SCATTER_GATHER)
+    assert np.abs(pair.compute(1, 0, cfg, ago=1) - ref["f"]).max() <= TOL_F
+    # descriptors come back in the potential's own layout whatever the kernel's padded shape is
+    G, dE = pair.descriptors(cfg)
+    assert G.shape == (cfg.nlocal, pot.nsf)
+    from oracle import restatement
+    parsed = read_potential(pf, elems)
+    o = restatement.compute(parsed, cfg, ntypes=len(elems), type_map=[0] + list(range(len(elems))), dump_G=True)
+    assert np.abs(G - o["G"]).max() <= 1e-9 * max(1.0, np.abs(o["G"]).max())
+    pair.clear()
+
+
+def test_two_elements_with_two_different_networks(tmp_path):
+    """The reference's FILE FORMAT cannot carry a second network (see test above), but its compute() selects weights per
+    element (fe_v2/src/pair_annp.cpp:114,181: all_annp[itype]).  Give the C ABI two different non-zero networks and a
+    non-trivial type -> element map (types 1,3 -> element 1, type 2 -> element 0) and compare with the pinned
+    restatement of that compute()."""
+    from meng_zhang_b200.pair import write_potential
+    from oracle import restatement
+    pot, _ = util.general_potential("two_elements")
+    assert np.abs(pot.weight_all[0] - pot.weight_all[1]).max() > 0.1
+    x, box = L.bcc(4, 4, 4)
+    types = np.random.default_rng(5).integers(1, 4, size=len(x)).astype(np.int32)
+    cfg = L.build_config(L.perturb(x, 0.05, 99), box, pot.cut, types=types, shuffle_rows=2)
+    pf = str(tmp_path / "two.ann")
+    write_potential(pf, pot)
+    pair = PairANNPGPU(ntypes=3)
+    pair.settings([])
+    pair.coeff(["*", "*", pf, "Cr", "Fe", "Cr"])
+    assert list(pair.map[1:]) == [0, 1, 0]           # pair_coeff order: Cr is element 0 of the style
+    pair.params = pot                                 # both networks, bypassing the single-block reader
+    pair.map[1:] = [1, 0, 1]
+    pair.init_style()
+    f = pair.compute(3, 1, cfg, ago=0)
+    o = restatement.compute(pot, cfg, ntypes=3, type_map=[0, 1, 0, 1], nthreads=2)
+    assert np.abs(pair.eatom - o["eatom"]).max() <= TOL_E
+    assert np.abs(f - o["f"]).max() <= TOL_F
+    assert np.abs(pair.virial - o["virial"]).max() <= TOL_V
+    # and the two networks really are different: swapping the map changes the answer
+    e0 = pair.eatom.copy()
+    pair.map[1:] = [0, 1, 0]
+    pair.init_style()
+    pair.compute(3, 0, cfg, ago=0)
+    assert np.abs(pair.eatom - e0).max() > 1e-3
+    pair.clear()
+
+
+def test_shapes_beyond_the_kernel_range_are_refused(tmp_path):
+    from meng_zhang_b200.pair import write_potential
+    pot, _ = util.general_potential("shape_16_24")
+    pot.ntsf, pot.nsf = 25, 41
+    pot.sfnor_cov = np.append(pot.sfnor_cov, pot.sfnor_cov[-1]); pot.sfnor_avg = np.append(pot.sfnor_avg, pot.sfnor_avg[-1])
+    w = np.zeros((1, pot.ntl - 1, pot.nnod, 41)); w[..., :40] = pot.weight_all
+    pot.weight_all = w
+    pf = str(tmp_path / "big.ann")
+    write_potential(pf, pot)
+    pair = PairANNPGPU(ntypes=1)
+    pair.settings([])
+    pair.coeff(["*", "*", pf, "Fe"])
+    with pytest.raises(capi.AnnpError) as ei:
+        pair.init_style()
+    assert ei.value.code == capi.EINVAL
+
+
+def test_atoms_that_outgrow_the_tile_take_the_overflow_pass(fe_pot_file):
+    """Device-resident mode sizes the first-pass shared-memory tile once per list (in-cutoff maximum + 12).  Atoms that
+    gain more neighbours than that inside the skin are redone by the overflow pass of the same step with a tile of the
+    list's longest row: compress the box by 8 % after the tile was sized (the 24-atom shell at 6.99 A moves inside Rc) and the
+    forces still match an evaluation that sized its tile for the compressed box."""
+    import torch
+    x, box = L.bcc(6, 6, 6)
+    x = L.perturb(x, 0.05, 3)
+    cfg = L.build_config(x, box, 6.5)
+    scale = 0.92
+    cfg2 = L.Config(nlocal=cfg.nlocal, nghost=cfg.nghost, x=cfg.x * scale, type=cfg.type, ghost_owner=cfg.ghost_owner, ilist=cfg.ilist,
+                    numneigh=cfg.numneigh, neigh=cfg.neigh, box=cfg.box * scale)
+    ref_pair = make_pair(fe_pot_file)
+    f_ref = ref_pair.compute(1, 0, cfg2, ago=0)                 # host mode: tile sized for the compressed positions
+    e_ref = ref_pair.eng_vdwl
+    assert ref_pair.stats().overflow_pass_atoms == 0
+    pair = make_pair(fe_pot_file)
+    pair.upload_neighbors(cfg)
+    Lb = capi.lib()
+    dev = torch.device("cuda")
+    typ = torch.as_tensor(cfg.type, dtype=torch.int32, device=dev)
+    f = torch.zeros((cfg.nall, 3), dtype=torch.float64, device=dev)
+    ev = torch.zeros(8, dtype=torch.float64, device=dev)
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def step(xs):
+        xd = torch.as_tensor(xs, dtype=torch.float64, device=dev)
+        rc = Lb.annp_b200_compute_device(pair.handle, cfg.nlocal, cfg.nghost, C.c_void_p(xd.data_ptr()), C.c_void_p(typ.data_ptr()), 1, 0,
+                                         C.c_void_p(f.data_ptr()), None, C.c_void_p(ev.data_ptr()), None, s)
+        assert rc == 0
+        torch.cuda.synchronize()
+        return f.cpu().numpy().copy(), float(ev[0])
+
+    step(cfg.x)                                                  # sizes the tile: 112-113 neighbours + 12
+    st = pair.stats()
+    cap0 = st.tile_capacity
+    assert st.overflow_pass_atoms == 0 and cap0 < 136
+    f2, e2 = step(cfg2.x)                                        # ~136 neighbours per atom now
+    st = pair.stats()                                            # no error: the step is complete
+    assert st.overflow_pass_atoms > 0 and st.max_neigh_cut > cap0
+    assert np.abs(f2 - f_ref).max() <= 1e-11 and abs(e2 - e_ref) <= 1e-9 * abs(e_ref)
+    assert st.tile_capacity > cap0                               # the next steps size the first pass for them
+    f3, e3 = step(cfg2.x)
+    assert pair.stats().overflow_pass_atoms == 0 and np.array_equal(f3, f2)
+    pair.clear(); ref_pair.clear()

@@ -182,3 +182,26 @@ def test_ni_forces_depend_on_neighbour_row_order_energies_do_not(ni_pot):
     assert np.abs(a["G"] - b["G"]).max() < 1e-12 and abs(a["eng_vdwl"] - b["eng_vdwl"]) < 1e-10
     d = np.abs(a["f"] - b["f"]).max()
     assert 1e-4 < d < 5e-2
+
+
+@pytest.mark.parametrize("name", util.GENERAL_CASES)
+def test_restatement_matches_reference_on_general_potentials(name, tmp_path, built):
+    """Other descriptor shapes, activations 1/2/3, a non-linear output layer, five layers, two element blocks: golden
+    answers of the unmodified reference on synthetic potentials (make_golden.py general).  The file is re-created with the
+    writer and parsed by the library's reader, which files every weight block under element 0 as the reference does
+    (fe_v2/src/pair_annp.cpp:455: the element index is reset on every line), so the two-element case runs with the LAST
+    block as element 0 and an all-zero network for element 1 on both sides."""
+    from meng_zhang_b200.pair import write_potential
+    cfg, elems, ref, pot = util.load_general_case(name)
+    pf = str(tmp_path / f"{name}.ann")
+    write_potential(pf, pot)
+    parsed = read_potential(pf, elems)
+    assert (parsed.npsf, parsed.ntsf, parsed.nnod, parsed.ntl, parsed.flagact) == (pot.npsf, pot.ntsf, pot.nnod, pot.ntl, pot.flagact)
+    if len(elems) > 1:
+        assert np.array_equal(parsed.weight_all[0], pot.weight_all[-1]) and not parsed.weight_all[1].any()
+    out = restatement.compute(parsed, cfg, ntypes=len(elems), type_map=[0] + list(range(len(elems))), vatom=True, nthreads=2)
+    assert out["eng_vdwl"] == ref["eng_vdwl"]
+    assert np.array_equal(out["eatom"], ref["eatom"])
+    assert np.array_equal(out["f"], ref["f"])
+    assert np.array_equal(out["virial"], ref["virial_pair"])
+    assert np.array_equal(out["vatom"], ref["vatom"])
