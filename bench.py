@@ -10,10 +10,12 @@ halo, force evaluation (pack, fused descriptor/MLP/force kernel with fixed-point
 reverse halo, integration.  N ranks = LAMMPS-style brick decomposition 1x1x1 / 2x1x1 / 2x2x1 / 2x2x2, one rank per
 GPU, halo exchange on device buffers over NCCL.
 
-value   device-resident MD (positions never leave HBM), CUDA-event timed, max over ranks
-e2e     the same force evaluation through the reference-facing host call annp_b200_compute (host x in
-        pinned memory -> device, forces/energy back to the host every step), i.e. what
-        PairANNPGPU::compute costs inside a host-driven LAMMPS
+value   device-resident MD (positions never leave HBM) with the deck's `neigh_modify every 5 delay 5 check yes`
+        displacement check inside the timed region, CUDA-event timed, max over ranks
+e2e     the same force evaluation through the class LAMMPS compiles: PairANNPB200::compute (meng_zhang_b200/lammps/
+        pair_annp_b200.cpp, registered as annp/gpu) hosted by the LAMMPS stand-in driver (oracle/_ref/plugin_annp_b200: shim
+        headers + driver, the class derives from the reference's own PairANNP) on the same atoms and the same list, x / f
+        held in ordinary malloc'd arrays as LAMMPS holds them, host->device and device->host copies inside every call
 --impl reference : the reference's own CPU pair style (oracle/_ref/ref_annp_fe, unmodified source) on the
         host cores, one process per core on spatial chunks of a bounded sample of the same lattice.
 """
@@ -32,18 +34,16 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 A_FE = 2.8553
 RC = 6.5
 SKIN = 2.0
 FLOP_TRIPLET, FLOP_PAIR, FLOP_MLP = 278.0, 168.0, 1560.0     # F_alg = 278 T + 168 N + 1560
-NCU_TRAFFIC_BYTES = 5.563e8                                  # profiles/r1c_force_kernel.md: 521.7 MB read + 34.7 MB written per launch
-# FP64 flops the kernel EXECUTES per atom-step at this workload, from the same capture: (2 x 7.324e9 DFMA + 0.934e9 DMUL +
-# 0.743e9 DADD warp instructions) x 30.87 active threads / 524 288 atoms.  The algorithmic count prices the
-# straightforward recompute formulation at 278 flops per triplet; the kernel needs ~150, so `frac` (algorithmic, the
-# contract's definition) can exceed 1 while the pipe itself is `executed.frac` busy with useful flops.
-NCU_EXECUTED_FLOP_PER_ATOM_STEP = 9.612e5
+# DRAM traffic and executed FP64 flops of ONE force-kernel launch at this workload come from the committed ncu capture
+# (profiles/force_kernel_ncu.json, written by scripts/summarize_ncu.py from the .ncu-rep; nothing is typed in here).  The
+# algorithmic count prices the straightforward recompute formulation at 278 flops per triplet; the kernel needs
+# ~150, so `frac` (algorithmic, the contract's definition) can exceed 1 while the pipe is `executed.frac` busy.
+NCU_JSON = os.path.join(ROOT, "profiles", "force_kernel_ncu.json")
 PUBLISHED_ATOM_STEPS_PER_S = 152880 * 1000 / 1789.44         # BASELINE.md section 1 (the reference's own 2-GPU log)
 
 
@@ -126,11 +126,148 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm)}
 
 
+def ncu_capture(natoms):
+    """(traffic bytes, executed flops per atom-step, source) of the committed ncu capture if it was taken at this workload."""
+    try:
+        with open(NCU_JSON) as fp:
+            js = json.load(fp)
+    except (OSError, ValueError):
+        return None, None, None
+    if js.get("atoms") != natoms:
+        return None, None, js.get("source")
+    return js["dram_bytes_read"] + js["dram_bytes_write"], js.get("fp64_flops_executed_per_atom"), js.get("source")
+
+
+def potential_file(args, tag):
+    """--potential: any `.ann` file of the reference's format; default: the Fe potential shipped with the package."""
+    if args.potential:
+        return args.potential
+    from meng_zhang_b200 import potentials
+    return potentials.write_fe_potential(os.path.join(tempfile.gettempdir(), f"annp_b200_bench_fe_{tag}.ann"))
+
+
+def plugin_e2e(md, pair, pot_file, ncalls, skip, device_index, pagelock=True):
+    """Pair::compute of the LAMMPS-facing C++ class on this rank's atoms (local + ghosts) and this rank's list, hosted by
+    the shim driver; returns (seconds per call over calls skip.., forces) or None when the binary is absent."""
+    import ctypes as C
+    import struct
+    from meng_zhang_b200 import capi
+    binary = os.path.join(ROOT, "oracle", "_ref", "plugin_annp_b200")
+    if not os.path.isfile(binary):
+        return None
+    if not os.access(binary, os.X_OK):
+        os.chmod(binary, 0o755)
+    Lb = capi.lib()
+    nlocal, nghost = md.nlocal, md.nghost
+    total = Lb.annp_b200_debug_neighbors(pair.handle, None, None)
+    if total < 0:
+        return None
+    off = np.zeros(nlocal + 1, dtype=np.int64)
+    neigh = np.zeros(max(total, 1), dtype=np.int32)
+    Lb.annp_b200_debug_neighbors(pair.handle, off.ctypes.data_as(capi.c_int64_p), neigh.ctypes.data_as(capi.c_int_p))
+    x = md.x.cpu().numpy()
+    typ = md.type.cpu().numpy().astype(np.int32)
+    with tempfile.TemporaryDirectory() as td:
+        fin, fout = os.path.join(td, "in.bin"), os.path.join(td, "out.bin")
+        with open(fin, "wb") as fp:
+            fp.write(struct.pack("<8i", nlocal, nghost, int(typ.max()), nlocal, 1, 0, ncalls, 0))
+            np.ascontiguousarray(x, dtype="<f8").tofile(fp)
+            typ.tofile(fp)
+            np.arange(nlocal, dtype="<i4").tofile(fp)
+            np.diff(off).astype("<i4").tofile(fp)
+            neigh[:total].tofile(fp)
+            np.zeros(nghost, dtype="<i4").tofile(fp)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(_physical_device(device_index)))
+        if not pagelock:
+            env["ANNP_B200_PAGELOCK"] = "0"
+        p = subprocess.run([binary, fin, fout, pot_file, "Fe"], capture_output=True, text=True, env=env)
+        if p.returncode != 0:
+            raise RuntimeError(f"plugin driver failed: {p.stderr[-1000:]}")
+        with open(fout, "rb") as fp:
+            nall, has_e, has_v, nc = struct.unpack("<4i", fp.read(16))
+            fp.read(8 + 48 + 8)
+            f = np.frombuffer(fp.read(nall * 24), dtype="<f8").reshape(nall, 3).copy()
+            fp.read(nall * 8 * has_e + nall * 48 * has_v)
+            per_call = np.frombuffer(fp.read(nc * 8), dtype="<f8").copy()
+    return float(per_call[skip:].mean()), f, per_call
+
+
+def _physical_device(local_index):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if local_index < len(ids):
+            return ids[local_index]
+    return local_index
+
+
+def multi_gpu_parity(rank, world, local_rank, dev, grid, pot_file, steps=20):
+    """Decomposed vs single-domain, outside the timed region (N > 1): 8x8x8 bcc cells per rank, forces of the first
+    evaluation and positions after `steps` NVE steps compared atom by atom with the same box on ONE GPU (rank 0)."""
+    import torch
+    import torch.distributed as dist
+    from meng_zhang_b200 import lattice as L
+    from meng_zhang_b200.md import DomainMD, rank_coords
+    from meng_zhang_b200.pair import PairANNPGPU
+
+    def make_pair():
+        pr = PairANNPGPU(ntypes=1, device=local_rank, skin=SKIN)
+        pr.settings([])
+        pr.coeff(["*", "*", pot_file, "Fe"])
+        pr.init_style()
+        return pr
+
+    coords = rank_coords(rank, grid)
+    x_all, box = L.bcc(8 * grid[0], 8 * grid[1], 8 * grid[2], A_FE)
+    x_all = L.wrap(L.perturb(x_all, 0.05, 5), box)
+    v_all = np.random.default_rng(9).normal(size=x_all.shape) * 2.0
+    v_all -= v_all.mean(axis=0)
+    lo = np.array([box[d] * coords[d] / grid[d] for d in range(3)])
+    hi = np.array([box[d] * (coords[d] + 1) / grid[d] for d in range(3)])
+    mine = np.all((x_all >= lo) & (x_all < hi), axis=1)
+    n_all = len(x_all)
+    pair = make_pair()
+    md = DomainMD(pair, x_all[mine], box, grid=grid, rank=rank, device=dev, skin=SKIN, gid_local=np.nonzero(mine)[0])
+    md.v = torch.as_tensor(v_all[mine], device=dev)
+    md.reneighbor()
+    md.compute(eflag=True)
+
+    def gathered(t):
+        g = torch.zeros((n_all, 3), dtype=torch.float64, device=dev)
+        g[md.gid] = t[: md.nlocal]
+        dist.all_reduce(g)
+        return g
+
+    f0 = gathered(md.f)
+    for _ in range(steps):
+        md.step()
+    x1 = gathered(md.x)
+    pair.stats()                      # raises if any step flagged an error on the device
+    out = None
+    if rank == 0:
+        pair1 = make_pair()
+        md1 = DomainMD(pair1, x_all, box, grid=(1, 1, 1), rank=0, device=dev, skin=SKIN)
+        md1.v = torch.as_tensor(v_all, device=dev)
+        md1.reneighbor()
+        md1.compute(eflag=True)
+        df = float((f0 - md1.f[:n_all]).abs().max())
+        for _ in range(steps):
+            md1.step()
+        boxd = torch.as_tensor(box, device=dev)
+        d = x1 - md1.x[:n_all]
+        d -= torch.round(d / boxd) * boxd
+        out = {"atoms": n_all, "steps": steps, "max_dF": df, "max_dx": float(d.abs().max()),
+               "what": "decomposed run vs the same box on one GPU: forces of the first evaluation (eV/A), positions after the NVE steps (A)"}
+        pair1.clear()
+    pair.clear()
+    dist.barrier()
+    return out
+
+
 def run_ours(args):
     import ctypes as C
     import torch
     import torch.distributed as dist
-    import util
     from meng_zhang_b200 import capi
     from meng_zhang_b200.md import DomainMD, decompose
     from meng_zhang_b200.pair import PairANNPGPU
@@ -155,7 +292,7 @@ def run_ours(args):
     x_local = lattice_block(cells, [coords[d] * cells for d in range(3)], 0.05, 1000 + rank)
     nlocal = len(x_local)
 
-    pot_file = util.write_fe_potential(os.path.join(tempfile.gettempdir(), f"annp_b200_bench_fe_{rank}.ann"))
+    pot_file = potential_file(args, rank)
     pair = PairANNPGPU(ntypes=1, device=local_rank, skin=SKIN)
     pair.settings([])
     pair.coeff(["*", "*", pot_file, "Fe"])
@@ -178,8 +315,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        md.step()
+    md.run(args.warmup, check_every=5)
     barrier()
     L.annp_b200_set_timing(pair.handle, 1)
     launches0 = pair.stats().kernel_launches
@@ -187,15 +323,32 @@ def run_ours(args):
     barrier()
     sampler.mark_begin()
     e0.record()
-    for _ in range(args.steps):
-        md.step()
+    # `run K` with the deck's `neigh_modify every 5 delay 5 check yes` (in.st_test:10-11): every 5th step the largest
+    # displacement since the last build is reduced (over ranks too) and read by the host, a rebuild follows if needed
+    md.run(args.steps, check_every=5)
     e1.record()
     barrier()
     sampler.mark_end()
     ms = e0.elapsed_time(e1)
+    rebuilds_timed = md.rebuilds
     clocks = sampler.stop() if rank == 0 else None
     st = pair.stats()
     L.annp_b200_set_timing(pair.handle, 0)
+    # one forced re-neighbouring (migration, ghost map, halo lists, device cell-list build), timed on its own: a 300 K
+    # crystal does not trigger one within a few hundred steps (the reference's published 1000-step run saw 2)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_r = time.perf_counter()
+    r0.record()
+    md.reneighbor()
+    r1.record()
+    torch.cuda.synchronize(dev)
+    reneigh_wall_ms = (time.perf_counter() - t_r) * 1e3
+    reneigh_ms = torch.tensor([max(r0.elapsed_time(r1), reneigh_wall_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(reneigh_ms, op=dist.ReduceOp.MAX)
+    reneigh_ms = float(reneigh_ms)
+    md.compute(eflag=True)
     launches = st.kernel_launches - launches0
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -210,40 +363,58 @@ def run_ours(args):
     achieved_tf = flop_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
     peak_tf = L.annp_b200_fp64_peak_tflops(pair.handle, 5)
 
-    # ---------------- e2e through the host-buffer C ABI (PairANNPGPU::compute path)
+    # ---------------- e2e: Pair::compute of the C++ class LAMMPS compiles, on this rank's atoms and list
     nall = md.nlocal + md.nghost
-    hx = torch.empty((nall, 3), dtype=torch.float64).pin_memory()
-    hx.copy_(md.x)
-    htype = torch.empty(nall, dtype=torch.int32).pin_memory()
-    htype.copy_(md.type)
-    hf = torch.empty((nall, 3), dtype=torch.float64).pin_memory()
-    eng = C.c_double(0.0)
-    dp = lambda t: C.cast(C.c_void_p(t.data_ptr()), capi.c_double_p)
-    ip = lambda t: C.cast(C.c_void_p(t.data_ptr()), capi.c_int_p)
-
-    def host_step():
-        rc = L.annp_b200_compute(pair.handle, md.nlocal, md.nghost, dp(hx), ip(htype), 1, 0, dp(hf), C.byref(eng), None, None, None)
-        if rc != 0:
-            raise RuntimeError(L.annp_b200_last_error(pair.handle).decode())
-
-    for _ in range(min(args.warmup, 3)):
-        host_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        host_step()
+    n_e2e = max(args.steps, 5)
+    skip = max(min(args.warmup, 3), 1)              # the first call also uploads the list (neighbor->ago == 0)
     torch.cuda.synchronize(dev)
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    res = plugin_e2e(md, pair, pot_file, n_e2e + skip, skip, local_rank)
+    e2e = None
+    if res is not None:
+        sec_call, f_plugin, per_call = res
+        # the plugin's forces against the device-resident path on the same atoms (one rank: the ghost rows fold onto
+        # their owners through the send list, as LAMMPS' reverse_comm would)
+        plugin_max_df = None
+        if world == 1:
+            md.compute(eflag=False)
+            fp = torch.as_tensor(f_plugin, device=dev)
+            folded = fp[: md.nlocal].clone()
+            folded.index_add_(0, md.send_index.long(), fp[md.nlocal:])
+            plugin_max_df = float((folded - md.f[: md.nlocal]).abs().max())
+            if not plugin_max_df <= 1e-9:
+                raise SystemExit(f"plugin path disagrees with the device-resident path: max|dF| = {plugin_max_df}")
+        t_e2e = torch.tensor([sec_call], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {"value": natoms_total / float(t_e2e), "unit": "atom-steps/s", "h2d_bytes_per_step": nall * 24, "d2h_bytes_per_step": nall * 24 + 56,
+               "path": "PairANNPB200::compute (meng_zhang_b200/lammps/pair_annp_b200.cpp, `pair_style annp/gpu`) in the LAMMPS stand-in "
+                       "driver oracle/_ref/plugin_annp_b200: atom->x / atom->f malloc'd as in LAMMPS and page-locked in place by the "
+                       "style, x up and f + energy down inside every call, types and list only at neighbor->ago == 0",
+               "ms_per_call": sec_call * 1e3, "calls_timed": n_e2e, "first_call_ms_incl_list_upload": float(per_call[0]) * 1e3,
+               "ratio_to_value": natoms_total / float(t_e2e) / value,
+               "max_dF_vs_device_resident_path": plugin_max_df}
+        if rank == 0 and world == 1 and not args.no_pageable:
+            res2 = plugin_e2e(md, pair, pot_file, 5 + skip, skip, local_rank, pagelock=False)
+            if res2 is not None:
+                e2e["pageable"] = {"value": natoms_total / res2[0], "ms_per_call": res2[0] * 1e3,
+                                   "what": "the same with ANNP_B200_PAGELOCK=0: x / f left pageable, every copy staged by the driver"}
     if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = natoms_total * args.steps / float(t_e2e)
+        e2e_note = "N independent plugin processes, one per GPU, Pair::compute only (LAMMPS' own halo exchange sits outside the pair style)"
+        if e2e is not None:
+            e2e["note"] = e2e_note
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = multi_gpu_parity(rank, world, local_rank, dev, grid, pot_file)
+        if rank == 0 and (parity["max_dF"] > 1e-9 or parity["max_dx"] > 1e-9):
+            raise SystemExit(f"multi-GPU parity check failed: {parity}")
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_baseline_reference(sample_cells=10, repeats=3)
+        cpu_base = cpu_baseline_reference(sample_cells=10, repeats=5, warmup=args.warmup)
     published = None
     if rank == 0 and world == 1 and not args.no_published_deck:
         published = run_published_deck(pot_file, dev)
 
+    ncu_traffic, ncu_flops, ncu_source = ncu_capture(nlocal) if world == 1 else (None, None, None)
     if rank == 0:
         out = {
             "metric": "atom-steps/sec (bcc Fe ANNP)", "value": value, "unit": "atom-steps/s", "n_gpus": world,
@@ -266,19 +437,23 @@ def run_ours(args):
                          "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at exactly this workload
                          # (profiles/r1c_force_kernel.md); algorithmic bytes are ~0.94 kB/atom = 0.49 GB
-                         "traffic": NCU_TRAFFIC_BYTES if (cells == 64 and world == 1) else None,
+                         "traffic": ncu_traffic, "traffic_source": ncu_source,
                          "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / (ms_total / args.steps),
                          "flop_per_atom_step": flop_per_launch / nlocal,
-                         "executed": ({"flop_per_atom_step": NCU_EXECUTED_FLOP_PER_ATOM_STEP,
-                                       "tflops": NCU_EXECUTED_FLOP_PER_ATOM_STEP * nlocal / (kern_ms * 1e-3) / 1e12,
-                                       "frac": NCU_EXECUTED_FLOP_PER_ATOM_STEP * nlocal / (kern_ms * 1e-3) / 1e12 / peak_tf,
-                                       "note": "FP64 flops actually issued (ncu opcode counts of profiles/r1c_force_kernel.md): the algorithmic "
+                         "executed": ({"flop_per_atom_step": ncu_flops,
+                                       "tflops": ncu_flops * nlocal / (kern_ms * 1e-3) / 1e12,
+                                       "frac": ncu_flops * nlocal / (kern_ms * 1e-3) / 1e12 / peak_tf,
+                                       "note": "FP64 flops actually issued (ncu opcode counts of the same capture): the algorithmic "
                                                "count credits 278 flops per triplet, the kernel executes ~150"}
-                                      if (cells == 64 and kern_ms > 0 and peak_tf > 0) else None),
+                                      if (ncu_flops and kern_ms > 0 and peak_tf > 0) else None),
                          "peak_source": "measured on this GPU by annp_b200_fp64_peak_tflops (pure DFMA loop); "
                                         "MEASURED_PEAKS.json has no FP64 entry"},
-            "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": nall * (24 + 4), "d2h_bytes_per_step": nall * 24 + 8,
-                    "path": "annp_b200_compute (host x/type -> device, f/energy -> host, every step)"},
+            "e2e": e2e,
+            "reneighbor": {"ms": reneigh_ms, "rebuilds_in_timed_region": int(rebuilds_timed), "check_every": 5,
+                           "per_step_ms_at_the_published_run_rate": reneigh_ms * 2 / 1000,
+                           "what": "one forced re-neighbouring at this size (atom migration, device ghost map and send lists, "
+                                   "device cell-list build), max over ranks; the displacement check itself is inside `value`"},
+            "parity": parity,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu_base,
@@ -339,12 +514,13 @@ def split_config(cfg, nparts):
     return parts
 
 
-def cpu_baseline_reference(sample_cells=10, repeats=1, cores=None):
+def cpu_baseline_reference(sample_cells=10, repeats=1, cores=None, warmup=1):
     """The reference CPU pair style (unmodified source, oracle/_ref/ref_annp_fe) on all host cores:
     `mpirun -np P` is emulated by P independent processes on spatial chunks (compute() has no
-    communication inside).  Returns the cpu_baseline object of the bench line."""
-    import util
-    from meng_zhang_b200 import lattice as L
+    communication inside).  Every process calls compute() warmup + repeats times on its chunk and times
+    each call itself (steady_clock around Pair::compute - no process start-up, no file I/O); a step costs what the
+    slowest process needs.  Returns the cpu_baseline object of the bench line."""
+    from meng_zhang_b200 import lattice as L, potentials
     from oracle import run_ref, restatement
     from concurrent.futures import ThreadPoolExecutor
     cores = cores or os.cpu_count() or 1
@@ -352,19 +528,20 @@ def cpu_baseline_reference(sample_cells=10, repeats=1, cores=None):
     box = np.array([sample_cells * A_FE] * 3)
     cfg = L.build_config(x, box, RC, SKIN)
     natoms = cfg.nlocal
-    pot_file = util.write_fe_potential(os.path.join(tempfile.gettempdir(), "annp_b200_bench_fe_cpu.ann"))
+    pot_file = potentials.write_fe_potential(os.path.join(tempfile.gettempdir(), "annp_b200_bench_fe_cpu.ann"))
     if run_ref.available("annp_fe"):
         parts = split_config(cfg, cores)
-        t0 = time.perf_counter()
-        for _ in range(repeats):
-            with ThreadPoolExecutor(max_workers=len(parts)) as ex:
-                list(ex.map(lambda c: run_ref.run_reference("annp_fe", c, pot_file, ["Fe"], eflag=1, vflag=0), parts))
-        dt = (time.perf_counter() - t0) / repeats
+        with ThreadPoolExecutor(max_workers=len(parts)) as ex:
+            outs = list(ex.map(lambda c: run_ref.run_reference("annp_fe", c, pot_file, ["Fe"], eflag=1, vflag=0, ncalls=warmup + repeats), parts))
+        per_step = np.max(np.stack([o["per_call_seconds"][warmup:] for o in outs]), axis=0)      # slowest process of every step
+        dt = float(per_step.mean())
         kind = "reference"
-        how = f"unmodified fe_v2/src/pair_annp.cpp, {len(parts)} processes x 1 thread on spatial chunks"
+        how = f"unmodified fe_v2/src/pair_annp.cpp, {len(parts)} processes x 1 thread on spatial chunks, timed inside the processes around Pair::compute"
     else:
         from meng_zhang_b200.pair import read_potential
         pot = read_potential(pot_file, ["Fe"])
+        for _ in range(warmup):
+            restatement.compute(pot, cfg, nthreads=cores)
         t0 = time.perf_counter()
         for _ in range(repeats):
             restatement.compute(pot, cfg, nthreads=cores)
@@ -372,30 +549,21 @@ def cpu_baseline_reference(sample_cells=10, repeats=1, cores=None):
         kind = "port"
         how = f"oracle/annp_oracle.c with {cores} OpenMP threads"
     return {"value": natoms / dt, "unit": "atom-steps/s", "cores": cores, "kind": kind,
-            "sample": f"{sample_cells}^3 bcc cells = {natoms} atoms of the same lattice (mean of {repeats} force evaluation(s), each incl. process start-up), {how}",
-            "seconds": dt}
+            "sample": f"{sample_cells}^3 bcc cells = {natoms} atoms of the same lattice ({repeats} timed force evaluation(s) after {warmup} warm-up), {how}",
+            "seconds": dt, "steps": repeats, "warmup": warmup}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    t_all = time.perf_counter()
-    vals = []
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_baseline_reference(sample_cells=args.ref_cells)
-    steps = max(1, args.steps)
-    base = None
-    for _ in range(steps):
-        base = cpu_baseline_reference(sample_cells=args.ref_cells)
-        vals.append(base["seconds"])
-        if time.perf_counter() - t_all > 240:
-            break
     natoms = 2 * args.ref_cells ** 3
-    v = natoms * len(vals) / sum(vals)
-    base["value"] = v
+    # bounded: one 2 000-atom evaluation costs ~0.4 s on 16 cores, so K + W calls stay within a few minutes up to K ~ 500
+    steps = max(1, min(args.steps, 500))
+    base = cpu_baseline_reference(sample_cells=args.ref_cells, repeats=steps, warmup=args.warmup)
+    v = base["value"]
     out = {"impl": "reference", "metric": "atom-steps/sec (bcc Fe ANNP)", "value": v, "unit": "atom-steps/s",
-           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": len(vals), "warmup": 1, "ms_per_step": 1e3 * sum(vals) / len(vals),
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * base["seconds"],
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"bcc Fe ANNP weak-scaling cell (BASELINE configs[4]); reference CPU pair style timed on a bounded "
                                   f"sample: {args.ref_cells}^3 cells = {natoms} atoms of the same lattice per step"},
@@ -413,6 +581,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-cells", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-memory variant of the e2e leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the decomposed-vs-single-GPU check (N > 1)")
+    ap.add_argument("--potential", default=None, help="`.ann` potential file (default: the Fe potential shipped in meng_zhang_b200/data)")
     ap.add_argument("--no-published-deck", action="store_true", help="skip the reference's own published deck (N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -400,6 +400,11 @@ int annp_b200_set_scatter(annp_b200_handle h, int mode);
  * test hook replacing the reference's printf debugging). Either pointer may be NULL. */
 int annp_b200_debug_descriptors(annp_b200_handle h, double *G, double *dE_dG);
 
+/* The neighbour list the handle currently holds (uploaded or built on the device), as CSR rows in ilist order: offsets
+ * [inum+1] and neigh [total], either may be NULL.  Returns the number of entries (>= 0) or a negative error code; call with
+ * NULLs first to size neigh.  Test / bench hook (device->host copy, synchronises the device). */
+long long annp_b200_debug_neighbors(annp_b200_handle h, int64_t *offsets, int *neigh);
+
 /* Host arithmetic, no device needed: the two basis-conversion matrices of the angular passes, each [ntsf][ntsf] row-major
  * (ntsf <= 24).  With y = (z+1)/2, z = cos(theta) and psi_{4b+i}(z) = T_{4b}(z) z^i:
  *     T_n(y) = sum_k cheb2mono[k*ntsf + n] z^k = sum_j blk2cheb[j*ntsf + n] psi_j(z)

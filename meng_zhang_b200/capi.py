@@ -150,6 +150,7 @@ PROTOTYPES = {
     "annp_b200_set_scatter": (C.c_int, [C.c_void_p, C.c_int]),
     "annp_b200_basis_matrices": (C.c_int, [C.c_int, c_double_p, c_double_p]),
     "annp_b200_debug_descriptors": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "annp_b200_debug_neighbors": (C.c_longlong, [C.c_void_p, c_int64_p, c_int_p]),
 }
 
 _lib = None

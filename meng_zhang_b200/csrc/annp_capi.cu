@@ -941,6 +941,18 @@ int annp_b200_set_timing(annp_b200_handle h, int enabled) {
   return ANNP_B200_OK;
 }
 
+long long annp_b200_debug_neighbors(annp_b200_handle h, int64_t *offsets, int *neigh) {
+  if (!h) return ANNP_B200_EINVAL;
+  if (!h->have_list) return fail(h, ANNP_B200_ESTATE, "no neighbour list");
+  if (cudaSetDevice(h->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return fail(h, ANNP_B200_ECUDA, "device synchronisation failed");
+  static_assert(sizeof(int64_t) == sizeof(long long), "row offsets are 64-bit");
+  if (offsets && cudaMemcpy(offsets, h->d_row_off.p, sizeof(long long) * ((size_t) h->inum + 1), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(h, ANNP_B200_ECUDA, "copying the row offsets failed");
+  if (neigh && h->total > 0 && cudaMemcpy(neigh, h->d_nbr.p, sizeof(int) * (size_t) h->total, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(h, ANNP_B200_ECUDA, "copying the neighbour rows failed");
+  return h->total;
+}
+
 int annp_b200_debug_descriptors(annp_b200_handle h, double *G, double *dE_dG) {
   if (!h) return ANNP_B200_EINVAL;
   if (!h->debug_desc) { h->debug_desc = true; return ANNP_B200_OK; }   // first call arms the capture

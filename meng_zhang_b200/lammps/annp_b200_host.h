@@ -42,7 +42,13 @@ struct RegisteredArray {
     release();
     ptr = p;
     bytes = n;
-    locked = p && n && annp_b200_host_register(p, n) == ANNP_B200_OK;
+    locked = p && n && pagelock_enabled() && annp_b200_host_register(p, n) == ANNP_B200_OK;
+  }
+  // ANNP_B200_PAGELOCK=0 leaves LAMMPS' arrays pageable (every copy is then staged by the CUDA driver)
+  static bool pagelock_enabled()
+  {
+    const char *s = getenv("ANNP_B200_PAGELOCK");
+    return !(s && s[0] == '0');
   }
   void release()
   {

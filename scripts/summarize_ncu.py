@@ -1,8 +1,12 @@
 """Turn ncu output (gpurun_out/) into the small text summaries committed under profiles/.
 
     python scripts/summarize_ncu.py launches gpurun_out/launches_r1.csv profiles/r1_launches.md
-    python scripts/summarize_ncu.py full gpurun_out/prof_force_r1d.ncu-rep profiles/r1_force_kernel.md
+    python scripts/summarize_ncu.py full gpurun_out/prof_force_r1d.ncu-rep profiles/r1_force_kernel.md [atoms]
+
+`full` also writes the numbers bench.py quotes (DRAM traffic per launch, FP64 flops executed per launch) as JSON next to
+the summary (same name, .json); bench.py reads profiles/force_kernel_ncu.json, a copy of the capture at its workload.
 """
+import json
 import csv
 import io
 import subprocess
@@ -53,7 +57,7 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 
-def full(rep, out):
+def full(rep, out, atoms=None):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
@@ -84,8 +88,24 @@ def full(rep, out):
         fp64 = sum(v for k, v in c.items() if k in ("DFMA", "DADD", "DMUL", "DSETP", "MUFU"))
         tens = sum(v for k, v in c.items() if k.startswith(("HMMA", "DMMA", "UTC", "IMMA")))
         lines += ["", f"FP64-pipe instructions: {fp64} ({100 * fp64 / te:.1f} % of all); tensor-pipe instructions: {tens}"]
+        val = lambda name: float(data[0][hdr.index(name)].replace(",", ""))
+        unit = lambda name: units[hdr.index(name)]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tpi = val("smsp__thread_inst_executed_per_inst_executed.ratio")
+        flops = (2 * c["DFMA"] + c["DMUL"] + c["DADD"]) * tpi
+        js = {"source": rep, "kernel": data[0][hdr.index("Kernel Name")],
+              "gpu_time_ms": val("gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}[unit("gpu__time_duration.sum")],
+              "dram_bytes_read": val("dram__bytes_read.sum") * scale[unit("dram__bytes_read.sum")],
+              "dram_bytes_write": val("dram__bytes_write.sum") * scale[unit("dram__bytes_write.sum")],
+              "warp_instructions": te, "threads_per_instruction": tpi,
+              "opcodes": {k: v for k, v in c.most_common(24)},
+              "fp64_flops_executed": flops, "atoms": int(atoms) if atoms else None,
+              "fp64_flops_executed_per_atom": flops / int(atoms) if atoms else None,
+              "fp64_pipe_active_pct": val("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+              "issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active")}
+        json.dump(js, open(out.rsplit(".", 1)[0] + ".json", "w"), indent=1)
     open(out, "w").write("\n".join(lines) + "\n")
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:])

@@ -3,12 +3,12 @@
     python tests/golden/make_golden.py
 
 Needs /root/reference and the binaries of `make -C oracle` (oracle/_ref/ref_*).  Writes
-  tests/golden/fe_potential.json   parameters of annp-gpu-lammps/fe_v2/fe_annp_potential_2.ann as parsed by
+  meng_zhang_b200/data/fe_potential.json   parameters of annp-gpu-lammps/fe_v2/fe_annp_potential_2.ann as parsed by
                                    the reference-compatible reader (numbers round-trip exactly; the test
                                    suite re-creates a `.ann` file from it with pair.write_potential)
   tests/golden/annp_fe_*.npz       inputs (x, type, ghosts, neighbour rows) and the reference's outputs
                                    (eng_vdwl, eatom, f, virial by pair tally and by f.r, vatom)
-  tests/golden/ni_potential.json, anna_potential.json, annp_ni_*.npz, anna_adp_*.npz
+  meng_zhang_b200/data/{ni,anna}_potential.json, tests/golden/annp_ni_*.npz, anna_adp_*.npz
                                    the same for the Ni copy of the style (ref_annp_ni) and for ANNA-ADP (ref_anna_adp)
   tests/golden/annp_general_*.npz  synthetic potentials (other shapes, activations, element counts) + the reference's answers
   tests/golden/fe_st.npz           the 152 880-atom slab of `performance test.zip` + its logged thermo values
@@ -31,6 +31,7 @@ from oracle.run_ref import run_reference  # noqa: E402
 REF = "/root/reference"
 POT = f"{REF}/annp-gpu-lammps/fe_v2/fe_annp_potential_2.ann"
 OUT = os.path.dirname(os.path.abspath(__file__))
+DATA = os.path.join(ROOT, "meng_zhang_b200", "data")      # the parsed potentials ship with the package
 
 
 def dump_potential():
@@ -42,7 +43,7 @@ def dump_potential():
     d["weight_all"] = pot.weight_all.tolist()
     d["bias_all"] = pot.bias_all.tolist()
     d["source"] = "annp-gpu-lammps/fe_v2/fe_annp_potential_2.ann (MPL-2.0), parsed numbers only"
-    with open(os.path.join(OUT, "fe_potential.json"), "w") as fp:
+    with open(os.path.join(DATA, "fe_potential.json"), "w") as fp:
         json.dump(d, fp)
 
 
@@ -130,7 +131,7 @@ def dump_ni_anna_potentials():
     for k in ("sfnor_cov", "sfnor_avg", "weight_all", "bias_all", "sym_coerad", "sym_coeang"):
         d[k] = getattr(pot, k).tolist()
     d["source"] = "annp-gpu-lammps/ni/ni_annp_potential_2.ann (MPL-2.0), parsed numbers only"
-    with open(os.path.join(OUT, "ni_potential.json"), "w") as fp:
+    with open(os.path.join(DATA, "ni_potential.json"), "w") as fp:
         json.dump(d, fp)
     pa = read_anna_potential(ANNA_POT, ["Fe"])
     d = {k: getattr(pa, k) for k in ("nelements", "ntl", "nhl", "nnod", "nout", "nsf", "npsf", "ntsf", "flagsym", "flagact",
@@ -138,7 +139,7 @@ def dump_ni_anna_potentials():
     for k in ("gparams", "weight_all", "bias_all"):
         d[k] = getattr(pa, k).tolist()
     d["source"] = "anna-gpu-lammps/bcc_fe/fe_adp_potential_2310.anna (MPL-2.0), parsed numbers only"
-    with open(os.path.join(OUT, "anna_potential.json"), "w") as fp:
+    with open(os.path.join(DATA, "anna_potential.json"), "w") as fp:
         json.dump(d, fp)
 
 

@@ -16,40 +16,9 @@ NI_CASES = ["fcc3_perturbed", "fcc334_hot", "cluster_ragged", "fcc3_two_types"]
 ANNA_CASES = ["bcc4_perfect", "bcc4_perturbed", "bcc334_hot", "cluster_ragged", "bcc4_two_types", "bcc8_perturbed"]
 
 
-def load_potential_json(name="fe_potential.json") -> AnnPotential:
-    with open(os.path.join(GOLDEN, name)) as fp:
-        d = json.load(fp)
-    d.pop("source", None)
-    for k in ("sfnor_cov", "sfnor_avg", "weight_all", "bias_all", "sym_coerad", "sym_coeang"):
-        if k in d:
-            d[k] = np.array(d[k])
-    return AnnPotential(**d)
-
-
-def load_anna_potential_json(name="anna_potential.json") -> AnnaPotential:
-    with open(os.path.join(GOLDEN, name)) as fp:
-        d = json.load(fp)
-    d.pop("source", None)
-    for k in ("gparams", "weight_all", "bias_all"):
-        d[k] = np.array(d[k])
-    return AnnaPotential(**d)
-
-
-def write_ni_potential(path) -> str:
-    write_potential(str(path), load_potential_json("ni_potential.json"),
-                    comment="ANN potential for Ni re-written from tests/golden/ni_potential.json")
-    return str(path)
-
-
-def write_anna_fe_potential(path) -> str:
-    write_anna_potential(str(path), load_anna_potential_json(),
-                         comment="ANNA-ADP potential for Fe re-written from tests/golden/anna_potential.json")
-    return str(path)
-
-
-def write_fe_potential(path) -> str:
-    write_potential(str(path), load_potential_json(), comment="ANN potential for Fe re-written from tests/golden/fe_potential.json")
-    return str(path)
+# the shipped potentials live in the package (meng_zhang_b200/data): bench.py and smoke() use them too
+from meng_zhang_b200.potentials import (load_anna_potential_json, load_potential_json, write_anna_fe_potential,  # noqa: E402,F401
+                                        write_fe_potential, write_ni_potential)
 
 
 def load_case(name, prefix="annp_fe"):
