@@ -315,7 +315,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    md.run(args.warmup, check_every=5)
+    md.run(max(args.warmup, 5), check_every=5)     # at least one displacement check in the warm-up
     barrier()
     L.annp_b200_set_timing(pair.handle, 1)
     launches0 = pair.stats().kernel_launches

@@ -62,6 +62,7 @@ extern "C" {
 #define ANNP_B200_ESTATE (-22)     /* call order (compute before neigh, ...)     */
 #define ANNP_B200_EOVERFLOW (-23)  /* an atom has more than MAX_NEIGH neighbours inside the cutoff */
 #define ANNP_B200_EIO (-24)        /* potential file unreadable / malformed      */
+#define ANNP_B200_ECOMM (-25)      /* NCCL unavailable or a NCCL call failed, see last_error */
 
 typedef struct annp_b200_handle_s *annp_b200_handle;
 
@@ -294,6 +295,48 @@ int annp_b200_set_halo(annp_b200_handle h, int nlocal, int nsend, const int *d_s
                        const double *d_send_shift, void *stream);
 int annp_b200_halo_pack(annp_b200_handle h, const double *d_x, double *d_sendbuf, void *stream);
 int annp_b200_halo_unpack_add(annp_b200_handle h, const double *d_recvbuf, double *d_f, void *stream);
+
+/* ---- ghost map on the device, halo exchange over NCCL ---------------------------------------------------------------------
+ * What LAMMPS' Comm::borders / forward_comm / reverse_comm do on host arrays over MPI (and the reference's library stages
+ * through the host around them, fe_v2/lib/lal_annp.cpp:310-312, 336-347), for runs that keep LAMMPS' brick decomposition
+ * with one rank per GPU.
+ *
+ * Ghost map (once per re-neighbouring).  The caller describes up to 26 SLOTS: slot k takes every local atom that lies within
+ * cutghost of the faces named by slot_dir[k] = (sx, sy, sz), s = +1: x >= hi - cutghost, -1: x < lo + cutghost, 0: any;
+ * slots are listed in the order their atoms are to appear in the send list (by destination rank, then direction).
+ *   send_lists_count  classifies the nlocal atoms at d_x (device) and returns the 26 slot counts - the only numbers of a
+ *                     re-neighbouring that travel to the host; the caller sizes the send list from them
+ *   send_lists_fill   writes send_index[m] / send_shift[m][3] (device) for all slots, entries of a slot in ascending atom
+ *                     index: the arguments of annp_b200_set_halo.  slot_shift[k][3] is the periodic image shift of slot k.
+ * Deterministic (two-level prefix sums, no atomics on the output order). */
+int annp_b200_send_lists_count(annp_b200_handle h, int nlocal, const double *d_x, const double *lo, const double *hi,
+                               double cutghost, int nslots, const int *slot_dir, int *slot_counts, void *stream);
+int annp_b200_send_lists_fill(annp_b200_handle h, const double *slot_shift, int *d_send_index, double *d_send_shift,
+                              void *stream);
+
+/* NCCL communicator of the handle: one rank (of the communicator) calls comm_unique_id and hands the 128 bytes to every
+ * rank by whatever it has (MPI_Bcast inside LAMMPS, torch.distributed in the stand-alone driver); every rank then calls
+ * comm_init.  nranks == 1 needs no id and no NCCL.  NCCL itself is taken from the process at run time (libnccl.so.2;
+ * ANNP_B200_NCCL_LIB names another file), so the library has no link-time dependency on it. */
+int annp_b200_comm_unique_id(char *id128);
+int annp_b200_comm_init(annp_b200_handle h, int nranks, int rank, const char *id128);
+void annp_b200_comm_destroy(annp_b200_handle h);
+/* per-rank atom counts of one exchange, after annp_b200_set_halo: send_counts[r] entries of the send list (which is ordered
+ * by destination) go to rank r, recv_counts[r] ghosts arrive from rank r (the ghost block is ordered by source rank) */
+int annp_b200_set_halo_peers(annp_b200_handle h, int nranks, const int *send_counts, const int *recv_counts);
+/* Comm::forward_comm: ghost block of d_x [nall][3] <- owners' positions (+ periodic shift): pack kernel and ONE grouped
+ * ncclSend / ncclRecv straight into the ghost rows (on one rank: the pack kernel writes them).
+ * Comm::reverse_comm: ghost rows of d_f go home and are added to the owners' rows in a fixed order (halo_unpack_add).
+ * Plain stream work, no host synchronisation: a whole MD step may be captured in a CUDA graph. */
+int annp_b200_halo_forward(annp_b200_handle h, double *d_x, void *stream);
+int annp_b200_halo_reverse(annp_b200_handle h, double *d_f, void *stream);
+/* sum of d_buf[0..n) over the ranks of the communicator, in place (thermo scalars, the 12 Nose-Hoover tensors) */
+int annp_b200_allreduce_sum(annp_b200_handle h, double *d_buf, int n, void *stream);
+
+/* d_out[0] = max over the nlocal atoms of |x - xref|^2 (device pointers): the quantity `neigh_modify check yes` compares
+ * with (skin/2)^2 (Neighbor::check_distance); one fused kernel, exact and order independent */
+int annp_b200_max_displacement_sq(annp_b200_handle h, int nlocal, const double *d_x, const double *d_xref, double *d_out,
+                                  void *stream);
 
 /* velocity-Verlet halves for the stand-alone MD loop (metal units; ftm2v = 1/(1.0364269e-4)):
  *   initial: v += dtf * f / m ; x += dt * v        final: v += dtf * f / m

@@ -22,7 +22,7 @@ VARIANT_FLAG_GENERIC = 0x100
 VARIANT_FLAG_NOPAIR = 0x200
 SCATTER_GATHER, SCATTER_FIXED = 0, 1
 
-OK, ENOMEM, ENODEVICE, EINVAL, ECUDA, ESTATE, EOVERFLOW, EIO = 0, -3, -4, -20, -21, -22, -23, -24
+OK, ENOMEM, ENODEVICE, EINVAL, ECUDA, ESTATE, EOVERFLOW, EIO, ECOMM = 0, -3, -4, -20, -21, -22, -23, -24, -25
 
 c_double_p = C.POINTER(C.c_double)
 c_int_p = C.POINTER(C.c_int)
@@ -130,9 +130,19 @@ PROTOTYPES = {
     "annp_b200_neigh_build": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, c_double_p, c_double_p, C.c_double, C.c_void_p]),
     "annp_b200_compute_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_send_lists_count": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_double_p, c_double_p, C.c_double, C.c_int, c_int_p, c_int_p, C.c_void_p]),
+    "annp_b200_send_lists_fill": (C.c_int, [C.c_void_p, c_double_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "annp_b200_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    "annp_b200_comm_destroy": (None, [C.c_void_p]),
+    "annp_b200_set_halo_peers": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_int_p]),
+    "annp_b200_halo_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_halo_reverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_allreduce_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "annp_b200_set_halo": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_halo_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_halo_unpack_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_max_displacement_sq": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_nve_initial": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_nve_final": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_nh_create": (C.c_int, [C.POINTER(NhConfig), c_double_p, c_double_p, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),

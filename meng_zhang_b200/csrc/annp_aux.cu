@@ -207,6 +207,20 @@ __global__ void k_halo_unpack_add(int nlocal, const long long *__restrict__ goff
     f[3 * (size_t) i] = fx; f[3 * (size_t) i + 1] = fy; f[3 * (size_t) i + 2] = fz;
   }
 }
+// out (bit pattern of a non-negative double, zeroed before the launch) = max_i |x_i - xref_i|^2: the re-neighbouring trigger
+// of `neigh_modify check yes` (Neighbor::check_distance).  Non-negative doubles order like their bit patterns, so the
+// integer atomicMax is exact and order independent.
+__global__ void k_max_disp2(int n, const double *__restrict__ x, const double *__restrict__ xref, unsigned long long *__restrict__ out) {
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double dx = x[3 * (size_t) i] - xref[3 * (size_t) i], dy = x[3 * (size_t) i + 1] - xref[3 * (size_t) i + 1],
+                 dz = x[3 * (size_t) i + 2] - xref[3 * (size_t) i + 2];
+    m = fmax(m, dx * dx + dy * dy + dz * dz);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long) __double_as_longlong(m));
+}
+
 __global__ void k_iota(int *p, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i;
 }
@@ -356,6 +370,15 @@ void aux_build_ghost_csr(const int *owner, int nghost, int nlocal, long long *go
 }
 void aux_halo_unpack_add(int nlocal, const long long *goff, const int *glist, const double *src, double *f, cudaStream_t s) {
   if (nlocal > 0) k_halo_unpack_add<<<grid_for(nlocal, 256), 256, 0, s>>>(nlocal, goff, glist, src, f);
+}
+
+void aux_max_disp2(int n, const double *x, const double *xref, double *out, cudaStream_t s) {
+  cudaMemsetAsync(out, 0, sizeof(double), s);
+  if (n > 0) k_max_disp2<<<grid_for(n, 256, 148 * 4), 256, 0, s>>>(n, x, xref, reinterpret_cast<unsigned long long *>(out));
+}
+
+void aux_iota(int *p, int n, cudaStream_t s) {
+  if (n > 0) k_iota<<<grid_for(n, 256), 256, 0, s>>>(p, n);
 }
 
 void aux_nve_initial(int n, double dt, double dtfm, double *x, double *v, const double *f, cudaStream_t s) {

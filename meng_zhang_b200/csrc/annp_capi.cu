@@ -1,7 +1,7 @@
 // annp_capi.cu -- the C ABI of libannp_b200.so (include/annp_b200.h): handle, device buffers and the
 // per-step launch sequence.  No CPU fallback: without an sm_100 device every entry point that needs
 // the GPU returns ANNP_B200_ENODEVICE.
-#include "annp_device.cuh"
+#include "annp_handle.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -35,6 +35,8 @@ void aux_build_ghost_csr(const int *owner, int nghost, int nlocal, long long *go
                          long long *tile_sum, cudaStream_t s);
 void aux_halo_unpack_add(int nlocal, const long long *goff, const int *glist, const double *src, double *f, cudaStream_t s);
 void aux_nve_initial(int n, double dt, double dtfm, double *x, double *v, const double *f, cudaStream_t s);
+void aux_max_disp2(int n, const double *x, const double *xref, double *out, cudaStream_t s);
+void aux_iota(int *p, int n, cudaStream_t s);
 void aux_nve_final(int n, double dtfm, double *v, const double *f, cudaStream_t s);
 int aux_ke_blocks(int n);
 void aux_kinetic(int n, const double *v, double half_mass, double *partial, double *out, cudaStream_t s);
@@ -51,25 +53,6 @@ void neigh_fill(const double *d_x, int nlocal, const double *lo, const int *n, c
                 NeighScratch sc, const long long *d_row_off, int *d_rows_tmp, int *d_rows, cudaStream_t s);
 
 namespace {
-
-// growable device allocation
-struct DevBuf {
-  void *p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t bytes, double slack = 1.1) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = (size_t) ((double) bytes * slack) + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
-    if (e == cudaSuccess) cap = want;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-  template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
-};
 
 __global__ void k_count_cut(const DevParams *prm, const double4 *__restrict__ xq, const int *__restrict__ ilist,
                             const long long *__restrict__ row_off, const int *__restrict__ nbr, int inum, int *__restrict__ maxn) {
@@ -116,71 +99,7 @@ __global__ void k_validate_list(const int *__restrict__ ilist, const long long *
 
 }    // namespace
 
-struct annp_b200_handle_s {
-  int device = 0;
-  int num_sms = 0;
-  cudaStream_t stream = nullptr;      // host-mode stream
-  DevParams hp;                       // host copy (weights/bias pointers are device pointers)
-  DevBuf d_params, d_weights, d_bias, d_cheb2mono, d_blk2cheb;
-  // neighbour list
-  bool have_list = false;
-  int inum = 0, nall_list = 0, max_row = 0;
-  long long total = 0;
-  DevBuf d_ilist, d_row_off, d_nbr, d_rev_off, d_rev_pos, d_centre_of, d_scratch_cnt, d_scratch_tmp, d_tile_sum;
-  // device neighbour build scratch
-  DevBuf d_cell_of, d_cell_cnt, d_cell_off, d_cell_atoms, d_row_cnt, d_small;
-  // per-step
-  DevBuf d_xq, d_fpair, d_facc, d_fself, d_vir_c, d_vpair, d_partial, d_counters, d_engvir, d_Gdbg, d_dEdbg, d_ovf_list;
-  // descriptor shape of the potential; hp.npsf / hp.ntsf / hp.nsf are the (possibly padded) shape of the kernel instantiation
-  int npsf_file = 0, ntsf_file = 0;
-  // how neighbour forces reach f: 1 = fixed-point integer atomics into d_facc (default),
-  // 0 = per-entry pair forces (d_fpair) summed by an ordered gather over the reverse map (annp_b200_set_scatter)
-  int scatter_fixed = 0;
-  bool have_reverse = false;
-  // host-mode staging
-  DevBuf d_x, d_type, d_f, d_eatom, d_vatom;
-  // ghosts
-  int g_nlocal = 0, g_nghost = 0;
-  const int *g_owner = nullptr;
-  const double *g_shift = nullptr;
-  DevBuf d_goff, d_glist, d_ke_partial;
-  int capacity = 0;
-  bool need_calibrate = true;
-  bool types_valid = false;           // host mode: d_type holds the types of the current atoms (annp_b200_compute with type == NULL)
-  void *pin_list = nullptr;           // pinned staging of the flattened host neighbour list (annp_b200_neigh)
-  size_t pin_list_cap = 0;
-  bool timing = false;
-  bool debug_desc = false;
-  static constexpr int kEvRing = 256;
-  cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
-  int ev_count = 0;                   // timed launches recorded and not yet collected
-  float last_force_ms = 0.f;
-  double force_ms_total = 0.0;
-  int force_samples = 0;
-  long long launches = 0;
-  DevCounters last_cnt;
-  std::string err;
-};
-
 namespace {
-
-int fail(annp_b200_handle h, int code, const std::string &msg) {
-  if (h) h->err = msg;
-  return code;
-}
-int cuda_fail(annp_b200_handle h, cudaError_t e, const char *where) {
-  return fail(h, e == cudaErrorMemoryAllocation ? ANNP_B200_ENOMEM : ANNP_B200_ECUDA,
-              std::string(where) + ": " + cudaGetErrorString(e));
-}
-#define CK(call)                                                         \
-  do {                                                                   \
-    cudaError_t e__ = (call);                                            \
-    if (e__ != cudaSuccess) return cuda_fail(h, e__, #call);             \
-  } while (0)
-
-void set_err(char *err, int errlen, const std::string &msg) {
-  if (err && errlen > 0) snprintf(err, (size_t) errlen, "%s", msg.c_str());
-}
 
 int round_capacity(int n) {
   int c = ((n + 15) / 16) * 16;
@@ -609,7 +528,9 @@ void annp_b200_clear(annp_b200_handle h) {
                     &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,
                     &h->d_eatom, &h->d_vatom, &h->d_goff, &h->d_glist, &h->d_ke_partial};
   for (DevBuf *b : bufs) b->release();
-  h->d_ovf_list.release();
+  annp_b200_comm_destroy(h);
+  DevBuf *more[] = {&h->d_ovf_list, &h->d_sl_tile_cnt, &h->d_sl_tile_off, &h->d_sl_tile_sum, &h->d_sendbuf, &h->d_recvbuf};
+  for (DevBuf *b : more) b->release();
   if (h->pin_list) cudaFreeHost(h->pin_list);
   for (int k = 0; k < annp_b200_handle_s::kEvRing; k++) {
     if (h->ev0[k]) cudaEventDestroy(h->ev0[k]);
@@ -628,7 +549,9 @@ double annp_b200_bytes(annp_b200_handle h) {
                           &h->d_eatom, &h->d_vatom, &h->d_goff, &h->d_glist, &h->d_ke_partial};
   double b = 0.0;
   for (const DevBuf *d : bufs) b += (double) d->cap;
-  return b + (double) h->d_ovf_list.cap;
+  const DevBuf *more[] = {&h->d_ovf_list, &h->d_sl_tile_cnt, &h->d_sl_tile_off, &h->d_sl_tile_sum, &h->d_sendbuf, &h->d_recvbuf};
+  for (const DevBuf *d : more) b += (double) d->cap;
+  return b;
 }
 
 const char *annp_b200_last_error(annp_b200_handle h) { return h ? h->err.c_str() : "null handle"; }
@@ -817,13 +740,8 @@ int annp_b200_neigh_build(annp_b200_handle h, int nlocal, int nall, const double
   CK(h->d_scratch_tmp.reserve(sizeof(int) * (size_t) std::max<long long>(total, 1)));
   neigh_fill(d_x, nlocal, bbox_lo, n, inv, cutneigh, sc, h->d_row_off.as<long long>(), h->d_scratch_tmp.as<int>(), h->d_nbr.as<int>(), s);
   h->launches += 2;
-  // ilist = 0..nlocal-1
-  {
-    std::vector<int> il((size_t) nlocal);
-    for (int i = 0; i < nlocal; i++) il[i] = i;
-    if (nlocal > 0) CK(cudaMemcpyAsync(h->d_ilist.p, il.data(), sizeof(int) * (size_t) nlocal, cudaMemcpyHostToDevice, s));
-    CK(cudaStreamSynchronize(s));
-  }
+  aux_iota(h->d_ilist.as<int>(), nlocal, s);      // ilist = 0..nlocal-1
+  h->launches += 1;
   return finish_list(h, s);
 }
 
@@ -892,6 +810,13 @@ int annp_b200_nve_final(annp_b200_handle h, int nlocal, double dt, double mass, 
     aux_kinetic(nlocal, d_v, 0.5 * mass * kMvv2e, h->d_ke_partial.as<double>(), d_ke, (cudaStream_t) stream);
     h->launches += 2;
   }
+  return ANNP_B200_OK;
+}
+
+int annp_b200_max_displacement_sq(annp_b200_handle h, int nlocal, const double *d_x, const double *d_xref, double *d_out, void *stream) {
+  if (!h || nlocal < 0 || !d_out || (nlocal > 0 && (!d_x || !d_xref))) return ANNP_B200_EINVAL;
+  aux_max_disp2(nlocal, d_x, d_xref, d_out, (cudaStream_t) stream);
+  h->launches += 1;
   return ANNP_B200_OK;
 }
 

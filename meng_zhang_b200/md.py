@@ -7,10 +7,12 @@ ghost forces every step, velocity-Verlet NVE.  Everything stays in HBM:
 
     nve_initial -> halo_pack -> [NCCL all_to_all_single] -> compute_device -> [NCCL] -> halo_unpack_add -> nve_final
 
-The exchange is one grouped NCCL send/recv over NVLink per direction (torch.distributed is only the
-plumbing); with one rank the "exchange" is the pack kernel writing straight into the ghost block.
-PyTorch is used for device allocations, streams and the process group - all arithmetic is in
-libannp_b200.so.
+The ghost map (which local atoms each neighbouring brick needs) is built on the device at every re-neighbouring
+(annp_b200_send_lists_*), and the exchange itself runs below the C ABI: one grouped ncclSend/ncclRecv over NVLink per
+direction on the handle's own NCCL communicator (annp_b200_halo_forward / _reverse); with one rank the "exchange" is the
+pack kernel writing straight into the ghost block.  PyTorch is used for device allocations, streams and to hand the NCCL
+unique id to the ranks - all arithmetic and all per-step communication is in libannp_b200.so, so a step is plain stream
+work and can be replayed as a CUDA graph on any number of ranks.
 """
 from __future__ import annotations
 
@@ -52,8 +54,38 @@ def coords_rank(c, grid):
     return (c[0] % px) + (c[1] % py) * px + (c[2] % pz) * px * py
 
 
+def send_slots(lo, hi, box, grid, coords, cutghost: float, periodic=(True, True, True)):
+    """The (up to 26) slots of the send list in list order: by destination rank, then by direction.  Returns
+    (dirs[int32 nslots,3], shifts[nslots,3], dests[nslots])."""
+    for d in range(3):
+        if hi[d] - lo[d] < cutghost:
+            raise ValueError("sub-domain thinner than the ghost cutoff: multi-hop halo not supported")
+    slots = []
+    for order, s in enumerate(itertools.product((-1, 0, 1), repeat=3)):
+        if s == (0, 0, 0):
+            continue
+        if any(s[d] != 0 and not periodic[d] and not (0 <= coords[d] + s[d] < grid[d]) for d in range(3)):
+            continue        # leaves the box through a free surface: no receiver
+        shift = np.zeros(3)
+        for d in range(3):
+            c = coords[d] + s[d]
+            if c >= grid[d]:
+                shift[d] = -box[d]
+            elif c < 0:
+                shift[d] = box[d]
+        slots.append((coords_rank([coords[d] + s[d] for d in range(3)], grid), order, s, shift))
+    slots.sort(key=lambda t: (t[0], t[1]))
+    dirs = np.array([t[2] for t in slots], dtype=np.int32).reshape(-1, 3)
+    shifts = np.array([t[3] for t in slots], dtype=np.float64).reshape(-1, 3)
+    dests = np.array([t[0] for t in slots], dtype=np.int64)
+    return np.ascontiguousarray(dirs), np.ascontiguousarray(shifts), dests
+
+
 def build_send_lists(x_local: np.ndarray, lo, hi, box, grid, coords, cutghost: float, periodic=(True, True, True)):
-    """Send entries for the 26 directions, grouped by destination rank.  A direction that leaves the box through a
+    """Host twin (numpy) of the device ghost map annp_b200_send_lists_count / _fill: the CPU tests check the
+    decomposition bookkeeping with it and the GPU tests check the kernels against it entry by entry.
+
+    Send entries for the 26 directions, grouped by destination rank.  A direction that leaves the box through a
     non-periodic face (`boundary m`/`f`/`s` of the decks: free surface) has no receiver and is skipped.
 
     Returns (index[int32 nsend], shift[nsend,3], send_counts[nranks]) with entries ordered by
@@ -143,6 +175,25 @@ class DomainMD:
         self.frozen_idx = None
         if frozen_local is not None and np.any(frozen_local):
             self.frozen_idx = torch.as_tensor(np.nonzero(np.asarray(frozen_local))[0], dtype=torch.int64, device=self.dev)
+        self.disp2 = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        self._init_comm()
+
+    def _init_comm(self):
+        """NCCL communicator of the handle (annp_b200_comm_init): rank 0 draws the unique id, torch.distributed only carries
+        its 128 bytes to the other ranks (inside LAMMPS an MPI_Bcast would)."""
+        ident = None
+        if self.world > 1:
+            import torch.distributed as dist
+            buf = C.create_string_buffer(128)
+            if self.rank == 0:
+                rc = self.L.annp_b200_comm_unique_id(buf)
+                if rc != 0:
+                    raise capi.AnnpError(rc, "NCCL unavailable: annp_b200_comm_unique_id failed")
+            t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(self.dev)
+            ranks = dist.get_process_group_ranks(self.group) if self.group is not None else None
+            dist.broadcast(t, src=ranks[0] if ranks else 0, group=self.group)
+            ident = bytes(t.cpu().numpy().tobytes())
+        self._ck(self.L.annp_b200_comm_init(self.h, self.world, self.rank, ident))
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -235,11 +286,20 @@ class DomainMD:
         fl = self.f[: self.nlocal] if self.f is not None else torch.zeros_like(xl)
         if migrate or self.gid is None:
             xl, fl = self._migrate(xl, fl)
-        xl_host = xl.cpu().numpy()
         cutghost = self.cut + self.skin
         if any(self.shrink_wrap):
             self._shrink_wrap_box(xl)
-        idx, shift, send_counts = build_send_lists(xl_host, self.lo, self.hi, self.box, self.grid, self.coords, cutghost, self.periodic)
+        # ghost map on the device: classify the local atoms against the (up to 26) slots; only the slot counts come back
+        xl = xl.contiguous()
+        dirs, shifts, dests = send_slots(self.lo, self.hi, self.box, self.grid, self.coords, cutghost, self.periodic)
+        nslots = len(dests)
+        slot_counts = np.zeros(max(nslots, 1), dtype=np.int32)
+        lo_h, hi_h = np.ascontiguousarray(self.lo, dtype=np.float64), np.ascontiguousarray(self.hi, dtype=np.float64)
+        self._ck(self.L.annp_b200_send_lists_count(self.h, self.nlocal, C.c_void_p(xl.data_ptr()), lo_h.ctypes.data_as(capi.c_double_p),
+                                                   hi_h.ctypes.data_as(capi.c_double_p), float(cutghost), nslots,
+                                                   dirs.ctypes.data_as(capi.c_int_p), slot_counts.ctypes.data_as(capi.c_int_p), self._stream()))
+        send_counts = np.zeros(self.world, dtype=np.int64)
+        np.add.at(send_counts, dests, slot_counts[:nslots])
         self.send_counts = [int(c) for c in send_counts]
         if self.world > 1:
             import torch.distributed as dist
@@ -249,21 +309,22 @@ class DomainMD:
             self.recv_counts = [int(c) for c in rc.cpu()]
         else:
             self.recv_counts = list(self.send_counts)
-        self.nsend = int(len(idx))
+        self.nsend = int(send_counts.sum())
         self.nghost = int(sum(self.recv_counts))
         nall = self.nlocal + self.nghost
-        self.send_index = torch.as_tensor(idx, dtype=torch.int32, device=self.dev)
-        self.send_shift = torch.as_tensor(shift, dtype=torch.float64, device=self.dev)
+        self.send_index = torch.empty(max(self.nsend, 1), dtype=torch.int32, device=self.dev)[: self.nsend]
+        self.send_shift = torch.empty((max(self.nsend, 1), 3), dtype=torch.float64, device=self.dev)[: self.nsend]
+        self._ck(self.L.annp_b200_send_lists_fill(self.h, shifts.ctypes.data_as(capi.c_double_p), C.c_void_p(self.send_index.data_ptr()),
+                                                  C.c_void_p(self.send_shift.data_ptr()), self._stream()))
         x = torch.empty((nall, 3), dtype=torch.float64, device=self.dev)
         x[: self.nlocal] = xl
         self.x = x
         self.f = torch.zeros((nall, 3), dtype=torch.float64, device=self.dev)
         self.f[: self.nlocal] = fl           # forces of the last evaluation: the next half kick uses them
-        if self.world > 1:
-            self.sendbuf = torch.empty((self.nsend, 3), dtype=torch.float64, device=self.dev)
-            self.recvbuf = torch.empty((self.nsend, 3), dtype=torch.float64, device=self.dev)
         self._ck(self.L.annp_b200_set_halo(self.h, self.nlocal, self.nsend, C.c_void_p(self.send_index.data_ptr()),
                                            C.c_void_p(self.send_shift.data_ptr()), self._stream()))
+        sc_h, rc_h = np.array(self.send_counts, dtype=np.int32), np.array(self.recv_counts, dtype=np.int32)
+        self._ck(self.L.annp_b200_set_halo_peers(self.h, self.world, sc_h.ctypes.data_as(capi.c_int_p), rc_h.ctypes.data_as(capi.c_int_p)))
         # ghost types travel once per re-neighbouring
         tl = self._type_local
         if self.world > 1:
@@ -284,29 +345,12 @@ class DomainMD:
 
     # ------------------------------------------------------------------ communication
     def forward_comm(self):
-        """Ghost positions <- owners (Comm::forward_comm)."""
-        if self.nsend == 0 and self.nghost == 0:
-            return
-        if self.world == 1:
-            self._ck(self.L.annp_b200_halo_pack(self.h, C.c_void_p(self.x.data_ptr()),
-                                                C.c_void_p(self.x[self.nlocal:].data_ptr()), self._stream()))
-        else:
-            import torch.distributed as dist
-            self._ck(self.L.annp_b200_halo_pack(self.h, C.c_void_p(self.x.data_ptr()),
-                                                C.c_void_p(self.sendbuf.data_ptr()), self._stream()))
-            dist.all_to_all_single(self.x[self.nlocal:], self.sendbuf, self.recv_counts, self.send_counts, group=self.group)
+        """Ghost positions <- owners (Comm::forward_comm): pack kernel + one grouped NCCL send/recv inside the library."""
+        self._ck(self.L.annp_b200_halo_forward(self.h, C.c_void_p(self.x.data_ptr()), self._stream()))
 
     def reverse_comm(self):
         """Ghost forces -> owners, deterministic ordered accumulation (Comm::reverse_comm)."""
-        if self.nsend == 0 and self.nghost == 0:
-            return
-        if self.world == 1:
-            src = self.f[self.nlocal:]
-        else:
-            import torch.distributed as dist
-            dist.all_to_all_single(self.recvbuf, self.f[self.nlocal:], self.send_counts, self.recv_counts, group=self.group)
-            src = self.recvbuf
-        self._ck(self.L.annp_b200_halo_unpack_add(self.h, C.c_void_p(src.data_ptr()), C.c_void_p(self.f.data_ptr()), self._stream()))
+        self._ck(self.L.annp_b200_halo_reverse(self.h, C.c_void_p(self.f.data_ptr()), self._stream()))
 
     # ------------------------------------------------------------------ force evaluation and integration
     def compute(self, eflag=False, vflag=False):
@@ -359,7 +403,8 @@ class DomainMD:
             return float(t)
 
         def energy_force():
-            moved = gmax((self.x[:n] - self._min_xref).square().sum(dim=1).max()) if n else 0.0
+            moved = self._moved_sq(self._min_xref)
+            self.check_device_flags()
             if moved > (0.5 * self.skin) ** 2:
                 self.reneighbor(migrate=False)
                 self._min_xref = self.x[:n].clone()
@@ -455,10 +500,9 @@ class DomainMD:
     def capture_step(self, nh: bool = False, eflag: bool = False):
         """Capture one MD step (NVE, or Nose-Hoover when nh=True) into a CUDA graph.  A step of a few thousand atoms is
         ~10 short kernels and is bound by launch latency, not by the GPU; replaying the captured graph issues them
-        with one call.  Valid until the next reneighbor() (buffers and list are re-created there); single rank only
-        (the NCCL halo exchange is left to eager mode)."""
-        if self.world != 1:
-            raise RuntimeError("capture_step: single-rank only")
+        with one call.  Valid until the next reneighbor() (buffers and list are re-created there).  With several ranks the
+        halo exchange (grouped ncclSend / ncclRecv issued by the library) and the Nose-Hoover all-reduce are captured too:
+        every rank replays its own graph and NCCL pairs the sends and receives as in eager mode."""
         fn = (lambda: self.step_nh(eflag=eflag)) if nh else (lambda: self.step(eflag=eflag))
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
@@ -528,8 +572,7 @@ class DomainMD:
 
     def _allreduce_red12(self):
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.red12, group=self.group)
+            self._ck(self.L.annp_b200_allreduce_sum(self.h, C.c_void_p(self.red12.data_ptr()), 12, self._stream()))
 
     def _nh_initial(self):
         s = self._stream()
@@ -583,10 +626,8 @@ class DomainMD:
             want = thermo_every > 0 and (n % thermo_every == 0 or n == nsteps)
             self._nh_initial()
             if check_every > 0 and n % check_every == 0:
-                moved = (self.x[: self.nlocal] - x_ref).square().sum(dim=1).max()
-                if self.world > 1:
-                    import torch.distributed as dist
-                    dist.all_reduce(moved, op=dist.ReduceOp.MAX, group=self.group)
+                moved = self._moved_sq(x_ref)
+                self.check_device_flags()
                 trigger = 0.5 * self.skin
                 if self.nh_pstat:
                     # Neighbor::check_distance with a changing box: the skin is reduced by the displacement of the two
@@ -625,8 +666,22 @@ class DomainMD:
         return pe, ke
 
     def max_displacement_since(self, x_ref: torch.Tensor) -> float:
-        d = (self.x[: self.nlocal] - x_ref).norm(dim=1).max()
-        return float(d)
+        return self._moved_sq(x_ref) ** 0.5
+
+    def _moved_sq(self, x_ref: torch.Tensor) -> float:
+        """max |x - x_ref|^2 over the atoms of ALL ranks (Neighbor::check_distance): one fused kernel, the maximum over
+        ranks, and the one host read the re-neighbouring decision needs."""
+        self._ck(self.L.annp_b200_max_displacement_sq(self.h, self.nlocal, C.c_void_p(self.x.data_ptr()), C.c_void_p(x_ref.data_ptr()),
+                                                      C.c_void_p(self.disp2.data_ptr()), self._stream()))
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.disp2, op=dist.ReduceOp.MAX, group=self.group)
+        return float(self.disp2)
+
+    def check_device_flags(self):
+        """Raises if a device-resident step since the last call flagged an error on the device (an atom beyond the largest
+        neighbour tile, a pair force outside the fixed-point range): annp_b200_get_stats reads and clears the sticky flags."""
+        self.pair.stats()
 
     def run(self, nsteps: int, check_every: int = 5, thermo_every: int = 0, log=None):
         """`run nsteps` with `neigh_modify every 5 delay 5 check yes` semantics (in.st_test:10-11):
@@ -643,11 +698,9 @@ class DomainMD:
             self._ck(self.L.annp_b200_nve_initial(self.h, self.nlocal, self.dt, self.mass, C.c_void_p(self.x.data_ptr()),
                                                   C.c_void_p(self.v.data_ptr()), C.c_void_p(self.f.data_ptr()), s))
             if check_every > 0 and n % check_every == 0:
-                moved = (self.x[: self.nlocal] - x_ref).square().sum(dim=1).max()
-                if self.world > 1:
-                    import torch.distributed as dist
-                    dist.all_reduce(moved, op=dist.ReduceOp.MAX, group=self.group)
-                if float(moved) > (0.5 * self.skin) ** 2:
+                moved = self._moved_sq(x_ref)
+                self.check_device_flags()        # the host is synchronised here anyway: read the device's sticky error flags
+                if moved > (0.5 * self.skin) ** 2:
                     self.reneighbor()
                     x_ref = self.x[: self.nlocal].clone()
                     rebuilds += 1

@@ -171,3 +171,35 @@ def test_atom_migration_keeps_every_atom_once_with_its_payload(world, tmp_path):
     mp.spawn(_migrate_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     allg = np.concatenate([np.load(tmp_path / f"gid{r}.npy") for r in range(world)])
     assert len(allg) == 4000 and np.array_equal(np.sort(allg), np.arange(4000))
+
+
+def test_send_slots_describe_the_host_send_lists():
+    """send_slots (what the device ghost map is told) and build_send_lists (the numpy twin) agree: applying the slots'
+    face tests in slot order reproduces the twin's index / shift / count arrays entry by entry."""
+    from meng_zhang_b200.md import send_slots
+    rng = np.random.default_rng(3)
+    box = np.array([40.0, 36.0, 44.0])
+    for grid, periodic in (((1, 1, 1), (True, True, True)), ((2, 2, 1), (True, False, True)), ((2, 2, 2), (True, True, True))):
+        nr = grid[0] * grid[1] * grid[2]
+        for rank in range(nr):
+            coords = rank_coords(rank, grid)
+            lo = np.array([box[d] * coords[d] / grid[d] for d in range(3)])
+            hi = np.array([box[d] * (coords[d] + 1) / grid[d] for d in range(3)])
+            x = lo + rng.random((500, 3)) * (hi - lo)
+            idx, shift, counts = build_send_lists(x, lo, hi, box, grid, coords, 8.5, periodic)
+            dirs, shifts, dests = send_slots(lo, hi, box, grid, coords, 8.5, periodic)
+            got_i, got_s, got_c = [], [], np.zeros(nr, dtype=np.int64)
+            for k in range(len(dests)):
+                m = np.ones(len(x), dtype=bool)
+                for d in range(3):
+                    if dirs[k, d] == 1:
+                        m &= x[:, d] >= hi[d] - 8.5
+                    elif dirs[k, d] == -1:
+                        m &= x[:, d] < lo[d] + 8.5
+                sel = np.nonzero(m)[0]
+                got_i.append(sel)
+                got_s.append(np.broadcast_to(shifts[k], (len(sel), 3)))
+                got_c[dests[k]] += len(sel)
+            assert np.array_equal(np.concatenate(got_i), idx)
+            assert np.array_equal(np.concatenate(got_s), shift)
+            assert np.array_equal(got_c, counts)
