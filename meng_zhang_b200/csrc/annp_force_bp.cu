@@ -711,7 +711,6 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
     if (lane == 0 && !a.work_list) {
       atomicMax(&a.cnt->max_neigh, N);
       atomicAdd(&a.cnt->sum_neigh, (unsigned long long) N);
-      atomicAdd(&a.cnt->sum_trip, (unsigned long long) N * (unsigned long long) (N > 0 ? N - 1 : 0) / 2ull);
     }
     if (N > C) {
       if (lane == 0) { annp_note_overflow(a, ii); a.fself[ii] = make_double4(0.0, 0.0, 0.0, 0.0); }
@@ -746,6 +745,9 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
       }
       Pv += __popc(m);
     }
+    // statistics: this kernel counts the CONTRIBUTING triplets T' (all three sides inside Rc), the quantity SURVEY 8d's
+    // flop formula for the Ni copy is written in
+    if (lane == 0 && !a.work_list) atomicAdd(&a.cnt->sum_trip, (unsigned long long) Pv);
     __syncwarp();
 
     // ---- 3. forward.  radial: one lane per neighbour; angular: one lane per contributing pair

@@ -12,7 +12,11 @@
     python -m torch.distributed.run --nproc-per-node 8 ... scripts/bench_configs.py --only 4
 
 One JSON line per configuration on rank 0: atom-steps/s (CUDA events, max over ranks), ms per step, temperature /
-pressure at the end as a sanity value.  Development aid + evidence for profiles/, not the driver's bench.
+pressure at the end as a sanity value, and the same `roofline` / `clocks` objects as bench.py for the configuration's force
+kernel (rank 0's launch): algorithmic flops of SURVEY 8d (Fe 278 T + 168 N + 1560; Ni 350 T' + 100 N + 4(27*24 + 24^2 + 24)
+with T' the contributing triplets; ANNA 86 T + 300 N + 432) over the CUDA-event kernel time against the measured FP64 peak,
+plus the algorithmic HBM bytes (list 4 B per entry, position 32 B, force 24 B, energy 8 B per atom) against the measured
+copy bandwidth of MEASURED_PEAKS.json.  Development aid + evidence for profiles/, not the driver's bench.
 """
 import argparse
 import json
@@ -26,9 +30,8 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-import util  # noqa: E402
-from meng_zhang_b200 import lattice as L, structures as S  # noqa: E402
+import bench  # noqa: E402  (ClockSampler)
+from meng_zhang_b200 import capi, lattice as L, potentials as util, structures as S  # noqa: E402
 from meng_zhang_b200.md import DomainMD, decompose, rank_coords  # noqa: E402
 from meng_zhang_b200.pair import PairANNPGPU  # noqa: E402
 from meng_zhang_b200.pair_anna import PairANNAADPGPU  # noqa: E402
@@ -74,8 +77,8 @@ def run_case(name, kind, x_all, box, mass, periodic, ensemble, steps, rank, worl
         stepper = md.step_nh
     for _ in range(5):
         stepper()
-    graph = bool(os.environ.get("ANNP_BENCH_GRAPH")) and world == 1
-    if graph:       # the step is ~10 short kernels: replay it as one CUDA graph (single rank only, valid until the next re-neighbouring)
+    graph = bool(os.environ.get("ANNP_BENCH_GRAPH"))
+    if graph:       # the step is ~10 short kernels (+ the grouped NCCL exchange): replay it as one CUDA graph per rank
         md.capture_step(nh=ensemble != "nve")
         stepper = lambda: md.replay(1)
         for _ in range(5):
@@ -83,18 +86,61 @@ def run_case(name, kind, x_all, box, mass, periodic, ensemble, steps, rank, worl
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    Lb = capi.lib()
+    pair.stats()
+    if not graph:
+        Lb.annp_b200_set_timing(pair.handle, 1)      # CUDA-event ring around the force kernel (eager launches only)
+    sampler = bench.ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         stepper()
     e1.record()
     torch.cuda.synchronize(dev)
+    if rank == 0:
+        sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t) / steps
     st = pair.stats()
+    Lb.annp_b200_set_timing(pair.handle, 0)
     extra = {}
+    if rank == 0:
+        kern_ms = st.force_kernel_ms_total / max(st.force_kernel_samples, 1)
+        n_loc, nbar = md.nlocal, st.avg_neigh_cut
+        if kind == "ni":
+            flop = 350.0 * st.sum_triplets + 100.0 * nbar * n_loc + 4.0 * (27 * 24 + 24 * 24 + 24) * n_loc
+            formula = "350 T' + 100 N + 4 (27*24 + 24^2 + 24), T' = contributing triplets counted by the kernel"
+        elif kind == "anna":
+            flop = 86.0 * st.sum_triplets + 300.0 * nbar * n_loc + 432.0 * n_loc
+            formula = "86 T + 300 N + 432, T = N(N-1)/2"
+        else:
+            flop = 278.0 * st.sum_triplets + 168.0 * nbar * n_loc + 1560.0 * n_loc
+            formula = "278 T + 168 N + 1560, T = N(N-1)/2"
+        list_entries = Lb.annp_b200_debug_neighbors(pair.handle, None, None)
+        hbm_bytes = 4.0 * list_entries + 32.0 * (md.nlocal + md.nghost) + (24.0 + 8.0) * n_loc
+        peak_tf = Lb.annp_b200_fp64_peak_tflops(pair.handle, 3)
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs"
+        except (OSError, KeyError, ValueError):
+            hbm_peak, hbm_src = 6468.6, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+        if kern_ms > 0:
+            tf = flop / (kern_ms * 1e-3) / 1e12
+            gbs = hbm_bytes / (kern_ms * 1e-3) / 1e9
+            extra["roofline"] = {"bound": "fp64", "kernel": {"ni": "annp_bp_pair_kernel<3,4>", "anna": "annp_force_kernel<9,19,1>"}.get(kind, "annp_force_kernel<9,19,0>"),
+                                 "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf > 0 else None,
+                                 "traffic": None, "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / ms,
+                                 "flop_per_atom_step": flop / n_loc, "flop_formula": formula,
+                                 "peak_source": "annp_b200_fp64_peak_tflops (DFMA loop on this GPU)",
+                                 "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                         "algorithmic_bytes_per_atom_step": hbm_bytes / n_loc, "peak_source": hbm_src}}
+        extra["clocks"] = clocks
     if ensemble != "nve":
         s = md.nh_state()
         extra = {"T": s.t_current, "p_bar": list(s.p_current[:]), "box": [s.boxhi[d] - s.boxlo[d] for d in range(3)]}
