@@ -211,6 +211,7 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
   a.cnt = h->d_counters.as<DevCounters>();
   a.inum = inum;
   a.capacity = h->capacity;
+  for (int k = 0; k < 17; k++) a.gp[k] = h->hp.gparams[k];
   a.work_list = nullptr;
   a.work_count = nullptr;
   a.work_ctr = &a.cnt->work;

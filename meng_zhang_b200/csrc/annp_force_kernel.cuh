@@ -137,9 +137,11 @@ __device__ __forceinline__ void angular_accumulate(double (&S)[NTSF], const doub
   }
 }
 
-// one out-of-line copy of pow(): inlined five times it is most of the ANNA instantiation's code and the kernel
-// stalls on instruction fetch (ncu r1b: stall_no_instruction 2.5 per issue)
-__device__ __noinline__ double anna_pow(double x, double y) { return pow(x, y); }
+// x^y for the ADP radial functions.  The reference calls pow() (pair_anna_adp.cpp:197,200); for the positive bases that
+// occur (r - r0 with r0 < 0, r / r1) exp(y log x) agrees with it to ~1e-15 relative, costs a third of CUDA's pow() and lets
+// powers of the SAME base share one logarithm.  Non-positive bases keep pow()'s semantics through one out-of-line copy
+// (inlined copies of pow() made the ANNA instantiation stall on instruction fetch: ncu r1b, stall_no_instruction 2.5).
+__device__ __noinline__ double anna_pow_slow(double x, double y) { return pow(x, y); }
 
 // ANNA-ADP tail (MODE 1): the descriptor of the centre atom is in sG (raw sums).  Reference: pair_anna_adp.cpp:166-272.
 //   network -> (d2, q2); per-neighbour sums rho, mu[3], lambda[3][3], E_rep with the smooth step psi = z^4/(1+z^4),
@@ -157,10 +159,25 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
   const double d2 = sH[(P.nlayers - 1) * P.nnod], q2 = sH[(P.nlayers - 1) * P.nnod + 1];
   if (a.G_dbg)
     for (int n = lane; n < P.nsf; n += 32) { a.G_dbg[(size_t) ii * P.nsf + n] = sG[n]; a.dEdG_dbg[(size_t) ii * P.nsf + n] = (n == 0) ? d2 : (n == 1 ? q2 : 0.0); }
-  const double *gp = P.gparams;
-  const double A0 = gp[0], yy = gp[1], gamma = gp[2], C0 = gp[3], c1F = gp[4], c2F = gp[5], V0 = gp[6], b1 = gp[7];
-  const double b2 = gp[8], delta = gp[9], r0 = gp[10], r1 = gp[11], hc = gp[12], d1 = gp[13], q1 = gp[14], d3 = gp[15], q3 = gp[16];
-  const double Rc = P.cut, hcinv = 1.0 / hc;
+  // A0, yy, gamma, C0, c1F, c2F, V0, b1, b2, delta, r0, r1, hc, d1, q1, d3, q3: kernel parameters (constant bank)
+#define A0 a.gp[0]
+#define yy a.gp[1]
+#define gamma a.gp[2]
+#define C0 a.gp[3]
+#define c1F a.gp[4]
+#define c2F a.gp[5]
+#define V0 a.gp[6]
+#define b1 a.gp[7]
+#define b2 a.gp[8]
+#define delta a.gp[9]
+#define r0 a.gp[10]
+#define r1 a.gp[11]
+#define hc a.gp[12]
+#define d1 a.gp[13]
+#define q1 a.gp[14]
+#define d3 a.gp[15]
+#define q3 a.gp[16]
+  const double Rc = P.cut, hcinv = 1.0 / hc, r1inv = 1.0 / r1;
   const double rep_coeff = V0 / (b2 - b1);
   double rho = 0, mx = 0, my = 0, mz = 0, lxx = 0, lyy = 0, lzz = 0, lxy = 0, lxz = 0, lyz = 0, erep = 0;
   for (int s = lane; s < N; s += 32) {
@@ -178,15 +195,22 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
     lxx = fma(w * x, x, lxx); lyy = fma(w * y, y, lyy); lzz = fma(w * z, z, lzz);
     lxy = fma(w * x, y, lxy); lxz = fma(w * x, z, lxz); lyz = fma(w * y, z, lyz);
     const double rz = r - r0, ez = exp(-gamma * rz);
-    const double zyy = A0 * anna_pow(rz, yy);
+    const double pz = r * r1inv;
+    double zyy, izb1, izb2;                                        // A0 rz^yy, pz^-b1, pz^-b2
+    if (rz > 0.0) {
+      zyy = A0 * exp(yy * log(rz));
+      const double lp = log(pz);                                   // r >= 1e-6 by the filter
+      izb1 = exp(-b1 * lp); izb2 = exp(-b2 * lp);
+    } else {
+      zyy = A0 * anna_pow_slow(rz, yy);
+      izb1 = 1.0 / anna_pow_slow(pz, b1); izb2 = 1.0 / anna_pow_slow(pz, b2);
+    }
     rho += stp * (zyy * ez * (1.0 + ez) + C0);
-    const double pz = r / r1;
-    const double zb1 = anna_pow(pz, b1), zb2 = anna_pow(pz, b2);
-    erep += stp * (rep_coeff * (b2 / zb1 - b1 / zb2) + delta);
+    erep += stp * (rep_coeff * (b2 * izb1 - b1 * izb2) + delta);
     accA[ps] = make_double2(ut, wt);
     accB[ps] = make_double2(ez, zyy);
-    accC[ps] = zb1;
-    sC[ps].x = zb2;                                                // dfc of the Chebyshev cutoff is not used by ANNA-ADP
+    accC[ps] = izb1;
+    sC[ps].x = izb2;                                               // dfc of the Chebyshev cutoff is not used by ANNA-ADP
   }
   rho = warp_sum(rho); mx = warp_sum(mx); my = warp_sum(my); mz = warp_sum(mz);
   lxx = warp_sum(lxx); lyy = warp_sum(lyy); lzz = warp_sum(lzz);
@@ -210,19 +234,20 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
     double fx = 0.0, fy = 0.0, fz = 0.0;
     const double x = r * A.x, y = r * A.y, z = r * B.x;
     if (!(r > Rc)) {
+      const double rinv = 1.0 / r;
       const double2 c1 = accA[ps], c2 = accB[ps];
-      const double ut = c1.x, wt = c1.y, ez = c2.x, zyy = c2.y, zb1 = accC[ps], zb2 = Cc.x;
+      const double ut = c1.x, wt = c1.y, ez = c2.x, zyy = c2.y, izb1 = accC[ps], izb2 = Cc.x;
       const double sx = (r - Rc) * hcinv, sx2 = sx * sx, sx4 = sx2 * sx2;
-      const double t1 = 1.0 + sx4;
-      const double stp = sx4 / t1;
-      const double dstp = 4.0 * sx2 * sx / (t1 * t1) * hcinv;
+      const double rt1 = 1.0 / (1.0 + sx4);
+      const double stp = sx4 * rt1;
+      const double dstp = 4.0 * sx2 * sx * (rt1 * rt1) * hcinv;
       const double rz = r - r0;
       const double gz = zyy * gamma;
       const double drho = ez * (1.0 + ez) * (zyy * (dstp + stp * yy / rz) - gz) + C0 * dstp - gz * ez * ez;
       const double d_emb = demb * drho;
-      const double pz = r / r1;
-      const double rep_t1 = rep_coeff * (b2 / zb1 - b1 / zb2) + delta;
-      const double d_rep = dstp * rep_t1 + stp * rep_coeff * ((b2 * b1 / r1) / pz * (-1.0 / zb1 + 1.0 / zb2));
+      const double rep_t1 = rep_coeff * (b2 * izb1 - b1 * izb2) + delta;
+      // d/dr [b2 pz^-b1 - b1 pz^-b2] = (b1 b2 / r) (pz^-b2 - pz^-b1)
+      const double d_rep = dstp * rep_t1 + stp * rep_coeff * (b2 * b1 * rinv * (izb2 - izb1));
       const double au = stp * (ut + d3), aw = 2.0 * stp * (wt + q3);
       const double dau = dstp * (ut + d3) + stp * (-d2 * ut);
       const double daw = dstp * (wt + q3) + stp * (-q2 * wt);
@@ -230,10 +255,9 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
       const double dl2 = daw * (lxy * x * y + lxz * x * z + lyz * y * z) * 2.0 + dl1;
       const double df1 = 0.5 * d_rep + d_emb + dau * (mx * x + my * y + mz * z) + dl2;
       const double df3 = f_v * (daw * r + aw);
-      const double rinv = 1.0 / r;
-      fx = df1 * x * rinv + aw * (y * lxy + z * lxz + x * lxx) + mx * au + x * df3;
-      fy = df1 * y * rinv + aw * (y * lyy + z * lyz + x * lxy) + my * au + y * df3;
-      fz = df1 * z * rinv + aw * (y * lyz + z * lzz + x * lxz) + mz * au + z * df3;
+      fx = df1 * A.x + aw * (y * lxy + z * lxz + x * lxx) + mx * au + x * df3;        // x / r = u_x
+      fy = df1 * A.y + aw * (y * lyy + z * lyz + x * lxy) + my * au + y * df3;
+      fz = df1 * B.x + aw * (y * lyz + z * lzz + x * lxz) + mz * au + z * df3;
     }
     if constexpr (FIXED) {                                            // f[j] += (fx, fy, fz), f[i] -=
       if (!annp_fix_add(a.facc, a.nbr[p0 + q] & ANNP_NEIGHMASK, fx, fy, fz)) atomicExch(&a.cnt->bad_force, 1);
@@ -262,6 +286,23 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
   }
   __syncwarp();
 #undef ROWPOS
+#undef A0
+#undef yy
+#undef gamma
+#undef C0
+#undef c1F
+#undef c2F
+#undef V0
+#undef b1
+#undef b2
+#undef delta
+#undef r0
+#undef r1
+#undef hc
+#undef d1
+#undef q1
+#undef d3
+#undef q3
 }
 
 // resident blocks per SM the register budget is set for: the shipped shapes (ntsf <= 20) run 4 blocks of 128 registers; the
@@ -352,11 +393,11 @@ __global__ void __launch_bounds__(kWarps * 32, annp_min_blocks(NTSF)) annp_force
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int q = base + 32 * u + lane;
-        jn[u] = (q < L) ? (a.nbr[p0 + q] & ANNP_NEIGHMASK) : -1;
+        jn[u] = (q < L) ? (annp_ld_list(a.nbr + p0 + q) & ANNP_NEIGHMASK) : -1;
       }
       double4 xn[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) xn[u] = (jn[u] >= 0) ? a.xq[jn[u]] : make_double4(0.0, 0.0, 0.0, 0.0);
+      for (int u = 0; u < 4; u++) xn[u] = (jn[u] >= 0) ? annp_ld_pos(a.xq + jn[u]) : make_double4(0.0, 0.0, 0.0, 0.0);
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int q = base + 32 * u + lane;

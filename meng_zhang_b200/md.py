@@ -178,6 +178,12 @@ class DomainMD:
         self.disp2 = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._init_comm()
 
+    def close(self):
+        """Drop the captured CUDA graph (it references the handle's NCCL communicator, which must not be destroyed under
+        it) and wait for the device: call before pair.clear() when capture_step was used."""
+        self._graph = None
+        torch.cuda.synchronize(self.dev)
+
     def _init_comm(self):
         """NCCL communicator of the handle (annp_b200_comm_init): rank 0 draws the unique id, torch.distributed only carries
         its 128 bytes to the other ranks (inside LAMMPS an MPI_Bcast would)."""
@@ -193,7 +199,19 @@ class DomainMD:
             ranks = dist.get_process_group_ranks(self.group) if self.group is not None else None
             dist.broadcast(t, src=ranks[0] if ranks else 0, group=self.group)
             ident = bytes(t.cpu().numpy().tobytes())
-        self._ck(self.L.annp_b200_comm_init(self.h, self.world, self.rank, ident))
+        # NCCL announces itself on stdout when NCCL_DEBUG is VERSION / WARN; stdout belongs to the caller's own output
+        # (bench.py prints exactly one JSON line), so the communicator is created with fd 1 pointing at stderr
+        import os
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            rc = self.L.annp_b200_comm_init(self.h, self.world, self.rank, ident)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        self._ck(rc)
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -282,6 +300,7 @@ class DomainMD:
         """Migrate atoms, rebuild send lists, ghosts and the device neighbour list from the current local positions.
         migrate=False keeps every atom on its rank, unwrapped and in place (used inside a line search, where the
         minimiser's direction vectors must stay aligned with the atoms)."""
+        self._graph = None          # a captured step refers to the buffers and the list replaced below
         xl = (self.x[: self.nlocal] if self.x is not None else self._x_local0)
         fl = self.f[: self.nlocal] if self.f is not None else torch.zeros_like(xl)
         if migrate or self.gid is None:

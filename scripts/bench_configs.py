@@ -143,7 +143,7 @@ def run_case(name, kind, x_all, box, mass, periodic, ensemble, steps, rank, worl
         extra["clocks"] = clocks
     if ensemble != "nve":
         s = md.nh_state()
-        extra = {"T": s.t_current, "p_bar": list(s.p_current[:]), "box": [s.boxhi[d] - s.boxlo[d] for d in range(3)]}
+        extra.update({"T": s.t_current, "p_bar": list(s.p_current[:]), "box": [s.boxhi[d] - s.boxlo[d] for d in range(3)]})
     nat = torch.tensor([float(md.nlocal)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(nat)
@@ -152,6 +152,7 @@ def run_case(name, kind, x_all, box, mass, periodic, ensemble, steps, rank, worl
                           "steps": steps, "ms_per_step": ms, "atom_steps_per_s": float(nat) / (ms * 1e-3),
                           "ns_per_day": 86400.0 / (ms * 1e-3) * 1e-6, "neighbors_in_cutoff": st.avg_neigh_cut,
                           "list_neighbors_max": st.max_neigh_list, **extra}), flush=True)
+    md.close()
     pair.clear()
 
 
