@@ -101,29 +101,6 @@ __device__ __forceinline__ void annp_note_overflow(const ForceArgs &a, int ii) {
   else atomicExch(&a.cnt->overflow, 1);
 }
 
-// Cache policy of the streaming inputs.  A list row is read once per step and a neighbour's position once per centre, with
-// no reuse inside the SM (centres are handed out by a global counter), while the network weights and the two basis
-// matrices (9 KB) are re-read by every atom: the streams bypass / leave L1 first so the parameters stay resident in what
-// the shared-memory carve-out leaves of it.
-#ifndef ANNP_CACHE_HINTS
-#define ANNP_CACHE_HINTS 1
-#endif
-__device__ __forceinline__ int annp_ld_list(const int *p) {
-#if ANNP_CACHE_HINTS
-  return __ldcs(p);
-#else
-  return *p;
-#endif
-}
-__device__ __forceinline__ double4 annp_ld_pos(const double4 *p) {
-#if ANNP_CACHE_HINTS
-  const double2 lo = __ldcg(reinterpret_cast<const double2 *>(p)), hi = __ldcg(reinterpret_cast<const double2 *>(p) + 1);
-  return make_double4(lo.x, lo.y, hi.x, hi.y);
-#else
-  return *p;
-#endif
-}
-
 // activation tables of the reference copies: Fe pair_annp.cpp:709-739, Ni ni/src/pair_annp.cpp:786-807,
 // ANNA-ADP pair_anna_adp.cpp:694-718 (3 and 4 = 1.7 tanh(0.3 x); only h is used there)
 __device__ __forceinline__ void annp_activation(int variant, int flag, double z, double &h, double &hd) {
@@ -163,8 +140,8 @@ __device__ __forceinline__ double annp_mlp_warp(const DevParams &P, const double
     const double *W = We + P.w_off[l];
     if (lane < nr) {
       double z = 0.0;
-      for (int cidx = 0; cidx < nc; cidx++) z = fma(__ldg(W + lane * nc + cidx), in[cidx], z);
-      z += __ldg(Be + P.b_off[l] + lane);
+      for (int cidx = 0; cidx < nc; cidx++) z = fma(W[lane * nc + cidx], in[cidx], z);
+      z += Be[P.b_off[l] + lane];
       double h, hd;
       annp_activation(P.variant, P.flagact[l], z, h, hd);
       sH[l * nnod + lane] = h;
@@ -182,7 +159,7 @@ __device__ __forceinline__ double annp_mlp_warp(const DevParams &P, const double
     const double *W = We + P.w_off[l];               // [nr][nnod]
     if (lane < nnod) {
       double s = 0.0;
-      for (int r = 0; r < nr; r++) s = fma(__ldg(W + r * nnod + lane), dcur[r], s);
+      for (int r = 0; r < nr; r++) s = fma(W[r * nnod + lane], dcur[r], s);
       dprev[lane] = s * sHd[(l - 1) * nnod + lane];
     }
     __syncwarp();
@@ -192,7 +169,7 @@ __device__ __forceinline__ double annp_mlp_warp(const DevParams &P, const double
   const double *W0 = We + P.w_off[0];                // [nr0][nsf]
   for (int n = lane; n < nsf; n += 32) {
     double s = 0.0;
-    for (int r = 0; r < nr0; r++) s = fma(__ldg(W0 + r * nsf + n), dcur[r], s);
+    for (int r = 0; r < nr0; r++) s = fma(W0[r * nsf + n], dcur[r], s);
     sdE[n] = s;
   }
   __syncwarp();
@@ -210,8 +187,8 @@ __device__ __forceinline__ void annp_mlp_forward_warp(const DevParams &P, const 
     const double *W = We + P.w_off[l];
     if (lane < nr) {
       double z = 0.0;
-      for (int cidx = 0; cidx < nc; cidx++) z = fma(__ldg(W + lane * nc + cidx), in[cidx], z);
-      z += __ldg(Be + P.b_off[l] + lane);
+      for (int cidx = 0; cidx < nc; cidx++) z = fma(W[lane * nc + cidx], in[cidx], z);
+      z += Be[P.b_off[l] + lane];
       double h, hd;
       annp_activation(P.variant, P.flagact[l], z, h, hd);
       sH[l * nnod + lane] = h;

@@ -393,11 +393,11 @@ __global__ void __launch_bounds__(kWarps * 32, annp_min_blocks(NTSF)) annp_force
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int q = base + 32 * u + lane;
-        jn[u] = (q < L) ? (annp_ld_list(a.nbr + p0 + q) & ANNP_NEIGHMASK) : -1;
+        jn[u] = (q < L) ? (a.nbr[p0 + q] & ANNP_NEIGHMASK) : -1;
       }
       double4 xn[4];
 #pragma unroll
-      for (int u = 0; u < 4; u++) xn[u] = (jn[u] >= 0) ? annp_ld_pos(a.xq + jn[u]) : make_double4(0.0, 0.0, 0.0, 0.0);
+      for (int u = 0; u < 4; u++) xn[u] = (jn[u] >= 0) ? a.xq[jn[u]] : make_double4(0.0, 0.0, 0.0, 0.0);
 #pragma unroll
       for (int u = 0; u < 4; u++) {
         const int q = base + 32 * u + lane;
