@@ -97,6 +97,43 @@ def test_ni_against_live_oracle_32000_atom_geometry_sample(ni_pot_file):
     pair.clear()
 
 
+def test_ni_forces_under_decomposition_follow_the_reference_on_each_ranks_own_list(ni_pot_file):
+    """The Ni copy's forces depend on the ORDER of a neighbour row (r_ik where r_jk is meant, ni/src/pair_annp.cpp:734-735),
+    so a decomposed run need not reproduce the single-domain forces (profiles/r1c_multi_gpu_check: 5e-3 eV/A) - the
+    only well-defined oracle for a rank is the reference evaluated on THAT rank's atoms and list.  Cut a box into 2 and
+    into 8 rank-like pieces (centre chunk + every atom its rows touch, renumbered, rows in the rank's own order) and pin
+    every piece to the restatement of the reference (bit-identical to the reference binary, tests/test_oracle.py); the
+    energies, which do not depend on the order, also add up to the single-domain energy."""
+    import bench
+    from oracle import restatement
+    pot = read_potential(ni_pot_file, ["Ni"])
+    x, box = L.fcc(5, 5, 5)
+    cfg = L.build_config(L.perturb(x, 0.07, 99), box, 6.5, shuffle_rows=3)
+    whole = make_ni(ni_pot_file)
+    whole.compute(3, 0, cfg, ago=0)
+    e_whole = whole.eng_vdwl
+    whole.clear()
+    for nparts in (2, 8):
+        e_sum = 0.0
+        for part in bench.split_config(cfg, nparts):
+            rng = np.random.default_rng(part.nlocal)
+            # a rank's list is in ITS bin order: reshuffle every row
+            off = part.offsets
+            neigh = part.neigh.copy()
+            for i in range(part.nlocal):
+                rng.shuffle(neigh[off[i]:off[i + 1]])
+            part = L.Config(nlocal=part.nlocal, nghost=part.nghost, x=part.x, type=part.type, ghost_owner=part.ghost_owner, ilist=part.ilist,
+                            numneigh=part.numneigh, neigh=neigh, box=part.box)
+            pair = make_ni(ni_pot_file)
+            f = pair.compute(3, 1, part, ago=0)
+            ref = restatement.compute_ni(pot, part, nthreads=2)
+            assert np.abs(f - ref["f"]).max() <= 1e-9
+            assert np.abs(pair.eatom - ref["eatom"]).max() <= 1e-10
+            e_sum += pair.eng_vdwl
+            pair.clear()
+        assert abs(e_sum - e_whole) <= 1e-9 * max(1.0, abs(e_whole))
+
+
 def test_anna_against_live_oracle_and_network_outputs(anna_pot_file):
     from oracle import restatement
     x, box = L.bcc(5, 4, 3)
