@@ -103,12 +103,42 @@ class Deck:
         return str(self.vars[name])
 
     def evaluate(self, expr):
-        """`equal`-style formulas of the decks: arithmetic over numbers, variables (v_name) and the keyword dt."""
+        """`equal`-style formulas of the decks: arithmetic over numbers, variables (v_name), the keyword dt and the functions
+        sqrt / exp / ln.  The formula is parsed into a syntax tree and only numbers, + - * / ^, unary minus, the known names
+        and calls of the three functions are evaluated; anything else (attributes, subscripts, other calls) is an error,
+        and exponents are bounded so a formula cannot stall the run."""
+        import ast
+        import operator
         expr = re.sub(r"v_(\w+)", lambda m: self._var(m.group(1)), expr)
-        names = {"dt": self.dt, "PI": math.pi, "sqrt": math.sqrt, "exp": math.exp, "ln": math.log}
-        if not re.fullmatch(r"[\w\s.+\-*/()^eE]*", expr):
-            raise DeckError(f"Invalid syntax in variable formula: {expr}")
-        return float(eval(expr.replace("^", "**"), {"__builtins__": {}}, names))
+        names = {"dt": self.dt, "PI": math.pi}
+        funcs = {"sqrt": math.sqrt, "exp": math.exp, "ln": math.log}
+        binops = {ast.Add: operator.add, ast.Sub: operator.sub, ast.Mult: operator.mul, ast.Div: operator.truediv}
+        bad = DeckError(f"Invalid syntax in variable formula: {expr}")
+
+        def ev(node):
+            if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)) and not isinstance(node.value, bool):
+                return float(node.value)
+            if isinstance(node, ast.Name) and node.id in names:
+                return float(names[node.id])
+            if isinstance(node, ast.UnaryOp) and isinstance(node.op, (ast.USub, ast.UAdd)):
+                v = ev(node.operand)
+                return -v if isinstance(node.op, ast.USub) else v
+            if isinstance(node, ast.BinOp) and type(node.op) in binops:
+                return binops[type(node.op)](ev(node.left), ev(node.right))
+            if isinstance(node, ast.BinOp) and isinstance(node.op, ast.Pow):
+                base, power = ev(node.left), ev(node.right)
+                if abs(power) > 1024.0:
+                    raise bad
+                return math.pow(base, power)
+            if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in funcs and len(node.args) == 1 and not node.keywords:
+                return funcs[node.func.id](ev(node.args[0]))
+            raise bad
+
+        try:
+            tree = ast.parse(expr.strip().replace("^", "**"), mode="eval")
+            return float(ev(tree.body))
+        except (SyntaxError, ValueError, ZeroDivisionError, OverflowError, RecursionError):
+            raise bad
 
     def run_file(self, path):
         self.cwd = os.path.dirname(os.path.abspath(path))

@@ -225,3 +225,18 @@ def test_kernel_arithmetic_restated_in_numpy_matches_the_oracle(fixed_point, fe_
     if fixed_point:       # every pair force moved by at most half a unit of 2^-43 eV/A: <= 112 * 5.7e-14 per atom
         f_plain, _ = K.compute(pot, cfg, c2m, b2c, fixed_point=False)
         assert 0.0 < np.abs(f - f_plain).max() <= 120 * 0.5 * 2.0 ** -43
+
+
+def test_deck_formulas_are_parsed_not_evaluated_as_python():
+    """`variable equal` / $(...) formulas: arithmetic, variables, dt, sqrt/exp/ln - and nothing else (no attribute access,
+    no other calls, bounded exponents)."""
+    from meng_zhang_b200.deck import Deck, DeckError
+    d = Deck.__new__(Deck)
+    d.vars, d.dt = {"a": "2.5", "n": "4"}, 0.001
+    assert d.evaluate("1+2*3") == 7.0
+    assert d.evaluate("v_a^2/dt") == 6250.0
+    assert d.evaluate("-sqrt(16)+exp(0)*v_n") == 0.0
+    assert abs(d.evaluate("ln(PI)") - 1.1447298858494002) < 1e-15
+    for bad in ("().__class__", "9^9^9^9", "__import__('os')", "a.b", "sqrt(1,2)", "[1][0]", "1 if 1 else 2", "1/0", "v_missing"):
+        with pytest.raises(DeckError):
+            d.evaluate(bad)
