@@ -420,6 +420,36 @@ def run_ours(args):
             if res2 is not None:
                 e2e["pageable"] = {"value": natoms_total / res2[0], "ms_per_call": res2[0] * 1e3,
                                    "what": "the same with ANNP_B200_PAGELOCK=0: x / f left pageable, every copy staged by the driver"}
+    if res is None:
+        # the stand-in driver binary is missing (it is built from the reference's sources, which this box does not have):
+        # time the C ABI call the class makes, annp_b200_compute, with page-locked host arrays
+        hx = torch.empty((nall, 3), dtype=torch.float64).pin_memory()
+        hx.copy_(md.x)
+        htype = torch.empty(nall, dtype=torch.int32).pin_memory()
+        htype.copy_(md.type)
+        hf = torch.empty((nall, 3), dtype=torch.float64).pin_memory()
+        eng = C.c_double(0.0)
+        dp = lambda t: C.cast(C.c_void_p(t.data_ptr()), capi.c_double_p)
+        ip = lambda t: C.cast(C.c_void_p(t.data_ptr()), capi.c_int_p)
+
+        def host_step(first):
+            rc = L.annp_b200_compute(pair.handle, md.nlocal, md.nghost, dp(hx), ip(htype) if first else None, 1, 0, dp(hf), C.byref(eng), None, None, None)
+            if rc != 0:
+                raise RuntimeError(L.annp_b200_last_error(pair.handle).decode())
+
+        host_step(True)
+        for _ in range(skip):
+            host_step(False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            host_step(False)
+        t_e2e = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e = {"value": natoms_total / float(t_e2e), "unit": "atom-steps/s", "h2d_bytes_per_step": nall * 24, "d2h_bytes_per_step": nall * 24 + 56,
+               "path": "annp_b200_compute with page-locked host x / f (oracle/_ref/plugin_annp_b200 not present on this box)",
+               "ms_per_call": float(t_e2e) * 1e3, "calls_timed": n_e2e, "ratio_to_value": natoms_total / float(t_e2e) / value}
     if world > 1:
         e2e_note = "N independent plugin processes, one per GPU, Pair::compute only (LAMMPS' own halo exchange sits outside the pair style)"
         if e2e is not None:

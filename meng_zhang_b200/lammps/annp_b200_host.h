@@ -118,6 +118,14 @@ struct HostBuffers {
   double bytes() const { return (double) (fbuf.n + ebuf.n + vbuf.n) * sizeof(double); }
 };
 
+// ANNP_B200_FORCE_ADD=1 : always stage the forces and ADD them to atom->f, even as the only pair style (decks in which
+// something else has written forces before Pair::compute, e.g. a fix with a pre_force method)
+inline bool force_add_requested()
+{
+  const char *s = getenv("ANNP_B200_FORCE_ADD");
+  return s && s[0] == '1';
+}
+
 // ANNP_B200_NEIGH=device : build the neighbour list on the GPU (the reference's `package gpu ... neigh yes`)
 inline bool device_neigh_requested()
 {

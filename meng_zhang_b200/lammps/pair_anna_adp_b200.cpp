@@ -87,7 +87,7 @@ void PairANNAADPB200::compute(int eflag, int vflag)
 
   // only pair style of a newton-on run: the device writes straight into LAMMPS' page-locked force array (see
   // annp_b200_host.h); otherwise the forces are staged (pair hybrid: added; newton off: folded by the style itself)
-  const bool direct = force->pair == this && force->newton_pair;
+  const bool direct = force->pair == this && force->newton_pair && !ANNP_B200_NS::force_add_requested();
   double *f0 = atom->f[0];
   double *fdst = f0;
   if (direct) hb.f.track(f0, sizeof(double) * 3 * (size_t) atom->nmax);

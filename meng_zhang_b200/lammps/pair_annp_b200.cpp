@@ -135,7 +135,7 @@ void PairANNPB200::compute(int eflag, int vflag)
 
   // Only pair style of the run: LAMMPS has zeroed f, the device writes the forces straight into the page-locked array
   // (the reference assigns f too, lal_annp.cpp:345-347).  As a sub-style of pair hybrid / overlay they are staged and added.
-  const bool sole = force->pair == this;
+  const bool sole = force->pair == this && !ANNP_B200_NS::force_add_requested();
   double *f0 = atom->f[0];
   double *fdst = f0;
   if (sole) hb.f.track(f0, sizeof(double) * 3 * (size_t) atom->nmax);
