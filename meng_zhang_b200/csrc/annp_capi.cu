@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 // ---- kernels' host entry points (annp_force.cu / annp_aux.cu / annp_neigh.cu)
@@ -619,9 +620,21 @@ int annp_b200_neigh(annp_b200_handle h, int inum, int nall, const int *ilist, co
     h->pin_list_cap = want;
   }
   int *flat = (int *) h->pin_list;
-  for (int ii = 0; ii < inum; ii++) {
-    const int i = ilist[ii];
-    if (numneigh[i] > 0) memcpy(flat + off[ii], firstneigh[i], sizeof(int) * (size_t) numneigh[i]);
+  // half a gigabyte of row copies at 524 288 atoms: a few host threads (LAMMPS runs one rank per GPU, the other cores idle)
+  const int nthreads = (int) std::max<int64_t>(1, std::min<int64_t>({8, (int64_t) std::thread::hardware_concurrency() / 2, off[inum] / (1 << 22)}));
+  auto copy_rows = [&](int lo, int hi) {
+    for (int ii = lo; ii < hi; ii++) {
+      const int i = ilist[ii];
+      if (numneigh[i] > 0) memcpy(flat + off[ii], firstneigh[i], sizeof(int) * (size_t) numneigh[i]);
+    }
+  };
+  if (nthreads <= 1) {
+    copy_rows(0, inum);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; t++)
+      pool.emplace_back(copy_rows, (int) ((int64_t) inum * t / nthreads), (int) ((int64_t) inum * (t + 1) / nthreads));
+    for (std::thread &t : pool) t.join();
   }
   return annp_b200_neigh_csr(h, inum, nall, ilist, off.data(), flat);
 }

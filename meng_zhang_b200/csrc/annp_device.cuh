@@ -211,6 +211,24 @@ __device__ __forceinline__ bool annp_fix_add(long long *facc, int j, double fx, 
   return ok;
 }
 
+// Sum 32 per-lane values of EVERY lane across the warp at once: on return lane n holds the warp total of w[n].  In the
+// round with lane mask m every lane keeps the half of its values that belongs to its side of the mask and hands the other
+// half over, so the number of live values halves each round: 16 + 8 + 4 + 2 + 1 = 31 shuffle-adds instead of 5 per value.
+// Fixed order -> deterministic.  (w is consumed.)
+__device__ __forceinline__ double warp_transpose_sum32(double (&w)[32], int lane) {
+#pragma unroll
+  for (int m = 16, cnt = 32; m >= 1; m >>= 1, cnt >>= 1) {
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int n = 0; n < cnt / 2; n++) {
+      const double send = up ? w[n] : w[n + cnt / 2];
+      const double keep = up ? w[n + cnt / 2] : w[n];
+      w[n] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  return w[0];
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

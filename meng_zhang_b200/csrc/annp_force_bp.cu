@@ -750,20 +750,39 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
     if (lane == 0 && !a.work_list) atomicAdd(&a.cnt->sum_trip, (unsigned long long) Pv);
     __syncwarp();
 
-    // ---- 3. forward.  radial: one lane per neighbour; angular: one lane per contributing pair
-    for (int m = 0; m < npsf; m++) {
-      double acc = 0.0;
-      for (int s = lane; s < N; s += 32) {
-        const BpGeom g = sN[s];
-        const double rm = g.r * CFLENGTH;
-        if (rm < Rc_rad) {
-          double fc, dfc;
-          bp_fc(rm, Rc_rad, fc, dfc);
-          acc += exp(-P.rad_eta[m] * rm * rm) * fc;
+    // ---- 3. forward.  radial: one lane per neighbour (N <= 32 here), the cutoff function and the npsf exponentials are
+    // computed ONCE and stay in registers for the backward pass; angular: one lane per contributing pair
+    constexpr int kRadReg = 3;                                   // radial components of the shipped file; other counts take
+    const bool rad_fast = npsf == kRadReg;                       // the component-by-component path
+    static_assert(kRadReg + NT <= 32, "descriptor sums must fit one transposing reduction");
+    double fcr = 0.0, dfcr = 0.0, rm_l = 0.0, er[kRadReg];
+#pragma unroll
+    for (int m = 0; m < kRadReg; m++) er[m] = 0.0;
+    if (rad_fast) {
+      if (lane < N) {
+        const BpGeom g = sN[lane];
+        rm_l = g.r * CFLENGTH;
+        if (rm_l < Rc_rad) {
+          bp_fc(rm_l, Rc_rad, fcr, dfcr);
+#pragma unroll
+          for (int m = 0; m < kRadReg; m++) er[m] = exp(-P.rad_eta[m] * rm_l * rm_l);
         }
       }
-      acc = warp_sum(acc);
-      if (lane == 0) sG[m] = (acc - P.sf_avg[m]) * P.sf_scale[m];
+    } else {
+      for (int m = 0; m < npsf; m++) {
+        double acc = 0.0;
+        for (int s = lane; s < N; s += 32) {
+          const BpGeom g = sN[s];
+          const double rm = g.r * CFLENGTH;
+          if (rm < Rc_rad) {
+            double fc, dfc;
+            bp_fc(rm, Rc_rad, fc, dfc);
+            acc += exp(-P.rad_eta[m] * rm * rm) * fc;
+          }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sG[m] = (acc - P.sf_avg[m]) * P.sf_scale[m];
+      }
     }
     double G[NT];
 #pragma unroll
@@ -789,10 +808,24 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
         }
       }
     }
+    if (rad_fast) {
+      // all npsf + NT <= 32 descriptor sums are reduced across the warp together (31 shuffle-adds instead of 5 per sum):
+      // slot n < npsf radial, npsf + n angular; lane n ends up with the total of slot n
+      double w[32];
 #pragma unroll
-    for (int n = 0; n < NT; n++) {
-      const double v = warp_sum(G[n]);
-      if (lane == 0) sG[npsf + n] = (v - P.sf_avg[npsf + n]) * P.sf_scale[npsf + n];
+      for (int n = 0; n < 32; n++) w[n] = 0.0;
+#pragma unroll
+      for (int m = 0; m < kRadReg; m++) w[m] = er[m] * fcr;
+#pragma unroll
+      for (int n = 0; n < NT; n++) w[kRadReg + n] = G[n];
+      const double tot = warp_transpose_sum32(w, lane);
+      if (lane < kRadReg + NT) sG[lane] = (tot - P.sf_avg[lane]) * P.sf_scale[lane];
+    } else {
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        const double v = warp_sum(G[n]);
+        if (lane == 0) sG[npsf + n] = (v - P.sf_avg[npsf + n]) * P.sf_scale[npsf + n];
+      }
     }
     __syncwarp();
 
@@ -813,12 +846,17 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
       const BpGeom A = sN[lane];
       const double ra_m = A.r * CFLENGTH;
       if (ra_m < Rc_rad) {
-        double fc, dfc;
-        bp_fc(ra_m, Rc_rad, fc, dfc);
         double acc = 0.0;
-        for (int m = 0; m < npsf; m++) {
-          const double et = P.rad_eta[m];
-          acc = fma(sCn[m], exp(-et * ra_m * ra_m) * (-fc * 2.0 * et * ra_m + dfc), acc);
+        if (rad_fast) {                                   // cutoff function and exponentials of stage 3
+#pragma unroll
+          for (int m = 0; m < kRadReg; m++) acc = fma(sCn[m], er[m] * (-fcr * 2.0 * P.rad_eta[m] * ra_m + dfcr), acc);
+        } else {
+          double fc, dfc;
+          bp_fc(ra_m, Rc_rad, fc, dfc);
+          for (int m = 0; m < npsf; m++) {
+            const double et = P.rad_eta[m];
+            acc = fma(sCn[m], exp(-et * ra_m * ra_m) * (-fc * 2.0 * et * ra_m + dfc), acc);
+          }
         }
         gx = -acc * A.ux; gy = -acc * A.uy; gz = -acc * A.uz;
       }

@@ -535,17 +535,7 @@ __global__ void __launch_bounds__(kWarps * 32, annp_min_blocks(NTSF)) annp_force
           const int c = 32 * rnd + n;                             // component reduced into lane n of this round
           w[n] = (c < NPSF) ? gr[c < NPSF ? c : 0] : (c < NSF ? S[(c >= NPSF && c < NSF) ? c - NPSF : 0] : 0.0);
         }
-#pragma unroll
-        for (int m = 16, cnt = 32; m >= 1; m >>= 1, cnt >>= 1) {
-          const bool up = (lane & m) != 0;
-#pragma unroll
-          for (int n = 0; n < cnt / 2; n++) {
-            const double send = up ? w[n] : w[n + cnt / 2];
-            const double keep = up ? w[n + cnt / 2] : w[n];
-            w[n] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-          }
-        }
-        const double tot = w[0];                                  // total of component 32 rnd + lane
+        const double tot = warp_transpose_sum32(w, lane);       // total of component 32 rnd + lane
         const int c = 32 * rnd + lane;
         if (c < NPSF) sG[c] = sScale[c] * tot - sScale[c] * sAvg[c];
         else if (c < NSF) sdE[c] = tot;                           // block-basis sums, parked in sdE (free until stage 3)
