@@ -385,6 +385,23 @@ def run_ours(args):
     achieved_tf = flop_per_launch / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
     peak_tf = L.annp_b200_fp64_peak_tflops(pair.handle, 5)
 
+    # ---------------- size-independent properties at the full size (the oracle cannot run 524 288 atoms): the net force
+    # vanishes (every pair force is applied +/-; fixed-point sums are exact, the residue is the rounding of the centre sums)
+    # and a second evaluation of the same positions is bit-identical (deterministic reductions)
+    md.compute(eflag=True)
+    f_a = md.f[: md.nlocal].clone()
+    e_a = md.engvir[0].clone()
+    md.compute(eflag=True)
+    net = f_a.sum(dim=0)
+    fmax = f_a.abs().max().reshape(1)
+    if world > 1:
+        dist.all_reduce(net)
+        dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+    invariants = {"net_force_eV_per_A": [float(v) for v in net], "max_abs_force_component": float(fmax),
+                  "repeat_evaluation_bit_identical": bool(torch.equal(f_a, md.f[: md.nlocal]) and torch.equal(e_a, md.engvir[0]))}
+    if max(abs(v) for v in invariants["net_force_eV_per_A"]) > 1e-6 or not invariants["repeat_evaluation_bit_identical"]:
+        raise SystemExit(f"full-size invariants violated: {invariants}")
+
     # ---------------- e2e: Pair::compute of the C++ class LAMMPS compiles, on this rank's atoms and list
     nall = md.nlocal + md.nghost
     n_e2e = max(args.steps, 5)
@@ -507,6 +524,7 @@ def run_ours(args):
                                    "device cell-list build), max over ranks; the displacement check itself is inside `value`",
                            "sustained": sustained},
             "parity": parity,
+            "invariants": invariants,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "cpu_baseline": cpu_base,

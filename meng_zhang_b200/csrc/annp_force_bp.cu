@@ -733,7 +733,7 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
         const BpGeom A = sN[pa], B = sN[pb];
         if (A.r * CFLENGTH < Rc && B.r * CFLENGTH < Rc) {
           const double ex = B.r * B.ux - A.r * A.ux, ey = B.r * B.uy - A.r * A.uy, ez = B.r * B.uz - A.r * A.uz;
-          ok = sqrt(ex * ex + ey * ey + ez * ez) * CFLENGTH < Rc;
+          ok = sqrt(ex * ex + ey * ey + ez * ez) * CFLENGTH < Rc;      // the very test bp_pair_prims applies
         }
       }
       const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -763,7 +763,8 @@ __global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const Forc
         const BpGeom g = sN[lane];
         rm_l = g.r * CFLENGTH;
         if (rm_l < Rc_rad) {
-          bp_fc(rm_l, Rc_rad, fcr, dfcr);
+          if (Rc_rad == Rc) { fcr = g.fc; dfcr = g.dfc; }          // same cutoff as the angular part (the shipped file): cached by the filter
+          else bp_fc(rm_l, Rc_rad, fcr, dfcr);
 #pragma unroll
           for (int m = 0; m < kRadReg; m++) er[m] = exp(-P.rad_eta[m] * rm_l * rm_l);
         }
