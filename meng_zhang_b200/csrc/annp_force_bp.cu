@@ -610,8 +610,11 @@ __global__ void __launch_bounds__(kWarps * 32, 3) annp_bp_fast_kernel(const Forc
 // per-pair slot; each neighbour then adds its slots in ascending partner order -> fixed summation order, no atomics.
 constexpr int kBpPairCap = 64;       // gradient slots per chunk (6 doubles each); more pairs are processed in chunks
 
+#ifndef ANNP_BP_PAIR_MINBLOCKS
+#define ANNP_BP_PAIR_MINBLOCKS 4
+#endif
 template <int NE, int NZ>
-__global__ void __launch_bounds__(kWarps * 32, 4) annp_bp_pair_kernel(const ForceArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, ANNP_BP_PAIR_MINBLOCKS) annp_bp_pair_kernel(const ForceArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = NE * NZ * 2;
   constexpr int C = 32;                                   // tile size this kernel is launched for
