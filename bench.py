@@ -530,7 +530,7 @@ def run_ours(args):
             "cpu_baseline": cpu_base,
             "published_deck": published,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), file=args.out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -640,7 +640,17 @@ def run_reference_arm(args):
                                   f"sample: {args.ref_cells}^3 cells = {natoms} atoms of the same lattice per step"},
            "cpu_baseline": base,
            "e2e": {"value": v, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    print(json.dumps(out), file=args.out, flush=True)
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL announces its version when NCCL_DEBUG is
+    VERSION / WARN, torch.distributed.run warns): everything the process writes to fd 1 from here on goes to stderr, and the
+    returned file object is the real stdout for the result line."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
@@ -658,6 +668,7 @@ def main():
     ap.add_argument("--potential", default=None, help="`.ann` potential file (default: the Fe potential shipped in meng_zhang_b200/data)")
     ap.add_argument("--no-published-deck", action="store_true", help="skip the reference's own published deck (N=1 only)")
     args = ap.parse_args()
+    args.out = claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -187,30 +187,38 @@ class DomainMD:
     def _init_comm(self):
         """NCCL communicator of the handle (annp_b200_comm_init): rank 0 draws the unique id, torch.distributed only carries
         its 128 bytes to the other ranks (inside LAMMPS an MPI_Bcast would)."""
+        import contextlib
+        import os
+        import sys
+
+        @contextlib.contextmanager
+        def stdout_to_stderr():
+            # NCCL announces itself on stdout when NCCL_DEBUG is VERSION / WARN; stdout belongs to the caller's own output
+            # (bench.py prints exactly one JSON line), so NCCL is initialised with fd 1 pointing at stderr
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                yield
+            finally:
+                os.dup2(saved, 1)
+                os.close(saved)
+
         ident = None
         if self.world > 1:
             import torch.distributed as dist
             buf = C.create_string_buffer(128)
             if self.rank == 0:
-                rc = self.L.annp_b200_comm_unique_id(buf)
+                with stdout_to_stderr():
+                    rc = self.L.annp_b200_comm_unique_id(buf)
                 if rc != 0:
                     raise capi.AnnpError(rc, "NCCL unavailable: annp_b200_comm_unique_id failed")
             t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(self.dev)
             ranks = dist.get_process_group_ranks(self.group) if self.group is not None else None
             dist.broadcast(t, src=ranks[0] if ranks else 0, group=self.group)
             ident = bytes(t.cpu().numpy().tobytes())
-        # NCCL announces itself on stdout when NCCL_DEBUG is VERSION / WARN; stdout belongs to the caller's own output
-        # (bench.py prints exactly one JSON line), so the communicator is created with fd 1 pointing at stderr
-        import os
-        import sys
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
+        with stdout_to_stderr():
             rc = self.L.annp_b200_comm_init(self.h, self.world, self.rank, ident)
-        finally:
-            os.dup2(saved, 1)
-            os.close(saved)
         self._ck(rc)
 
     # ------------------------------------------------------------------ helpers
