@@ -2,8 +2,8 @@
 
     python scripts/bench_variants.py [--ni-cells 20] [--anna-cells 40] [--steps 10]
 
-Prints one JSON line per variant: host-call atom-steps/s (annp_b200_compute, pinned-less numpy buffers) and the
-force kernel's CUDA-event time.
+Prints one JSON line per variant: host-call atom-steps/s (annp_b200_compute, pinned-less numpy buffers), the force
+kernel's CUDA-event time and the time of one Pair::compute of the LAMMPS-facing C++ class (page-locked in place).
 """
 import argparse
 import json
@@ -23,7 +23,17 @@ from meng_zhang_b200.pair_anna import PairANNAADPGPU  # noqa: E402
 from test_gpu_parity import build_large_config  # noqa: E402
 
 
-def run(kind, pair, cfg, steps):
+def plugin_call_ms(binary, cfg, pot, elem, steps):
+    """Pair::compute of the LAMMPS-facing C++ class (oracle/_ref/plugin_*: shim driver hosting PairANNPB200 / PairANNAADPB200,
+    x / f malloc'd and page-locked in place) timed inside the driver; None when the binary is absent."""
+    from oracle import run_ref
+    if not run_ref.available(binary):
+        return None
+    out = run_ref.run_reference(binary, cfg, pot, [elem], eflag=1, vflag=0, ncalls=steps + 3)
+    return float(out["per_call_seconds"][3:].mean() * 1e3)
+
+
+def run(kind, pair, cfg, steps, plugin=None):
     lib = capi.lib()
     t = time.perf_counter()
     pair.compute(1, 0, cfg, ago=0)
@@ -42,7 +52,8 @@ def run(kind, pair, cfg, steps):
                       "host_call_ms": dt * 1e3, "host_call_atom_steps_per_s": cfg.nlocal / dt,
                       "force_kernel_ms": st.force_kernel_ms_total / max(st.force_kernel_samples, 1),
                       "kernel_atom_steps_per_s": cfg.nlocal / (st.force_kernel_ms_total / max(st.force_kernel_samples, 1) * 1e-3),
-                      "first_call_with_list_upload_ms": t_first * 1e3, "E_per_atom": pair.eng_vdwl / cfg.nlocal}), flush=True)
+                      "first_call_with_list_upload_ms": t_first * 1e3, "E_per_atom": pair.eng_vdwl / cfg.nlocal,
+                      "plugin_call_ms": plugin_call_ms(*plugin, steps) if plugin else None}), flush=True)
 
 
 def main():
@@ -59,7 +70,7 @@ def main():
         pair.settings([])
         pair.coeff(["*", "*", pot, "Ni"])
         pair.init_style()
-        run("ni", pair, cfg, a.steps)
+        run("ni", pair, cfg, a.steps, plugin=("plugin_annp_ni_b200", cfg, pot, "Ni"))
         pair.clear()
     if a.anna_cells > 0:
         pot = util.write_anna_fe_potential("/tmp/annp_b200_bv_anna.anna")
@@ -69,7 +80,7 @@ def main():
         pair.settings([])
         pair.coeff(["*", "*", pot, "Fe"])
         pair.init_style()
-        run("anna_adp", pair, cfg, a.steps)
+        run("anna_adp", pair, cfg, a.steps, plugin=("plugin_anna_adp_b200", cfg, pot, "Fe"))
         pair.clear()
 
 
