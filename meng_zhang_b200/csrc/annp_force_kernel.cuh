@@ -47,11 +47,15 @@
 #ifndef ANNP_MINBLOCKS
 #define ANNP_MINBLOCKS 4
 #endif
-#ifdef ANNP_EXP_UNROLL2
-#define ANNP_STEP_UNROLL _Pragma("unroll 2")
-#else
-#define ANNP_STEP_UNROLL _Pragma("unroll 1")
+// unroll factors of the two triplet step loops (kernel experiments: -DANNP_UNROLL_FWD=2 / -DANNP_UNROLL_BWD=2)
+#ifndef ANNP_UNROLL_FWD
+#define ANNP_UNROLL_FWD 2      // same-box A/B at the bench size: 24.16 -> 24.02 ms (3: 24.22, 4: 24.64; backward 2: 24.35)
 #endif
+#ifndef ANNP_UNROLL_BWD
+#define ANNP_UNROLL_BWD 1
+#endif
+#define ANNP_PRAGMA_(x) _Pragma(#x)
+#define ANNP_PRAGMA(x) ANNP_PRAGMA_(x)
 
 namespace {
 
@@ -100,7 +104,7 @@ __device__ __forceinline__ Unit make_unit(const Sched &sc, int pass, int lane) {
   const int v = pass * 32 + lane;
   const int M = sc.M;
   u.active = v < M * sc.Q;
-  u.seg = v / M;
+  u.seg = v / M;      // (a multiply-high by a per-atom reciprocal instead of this division measured 0.5 % SLOWER)
   u.m = v - u.seg * M;
   if (!u.active) { u.seg = 0; u.m = 0; }
   u.elo = 1 + u.seg * sc.Hs;
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(kWarps * 32, annp_min_blocks(NTSF)) annp_force
         angular_accumulate<NTSF>(S, fma(A2.x, Ak.x, fma(A2.y, Ak.y, B2.x * Bk.x)), f2 * Bk.y);
         Ak = Akn; Bk = Bkn;
       };
-      ANNP_STEP_UNROLL
+      ANNP_PRAGMA(unroll ANNP_UNROLL_FWD)
       for (; t < end; t++) step();
     }
     // warp reduction, scaling and centring (pair_annp.cpp:178-180).  All nsf <= 32 sums are reduced TOGETHER by a
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(kWarps * 32, annp_min_blocks(NTSF)) annp_force
         __syncwarp();
         kp = kpn; Ak = Akn; Bk = Bkn;
       };
-      ANNP_STEP_UNROLL
+      ANNP_PRAGMA(unroll ANNP_UNROLL_BWD)
       for (; t < end; t++) step();
       // flush the row side; the same row pair can sit in several lanes (segments) -> one segment at a time
       for (int g = 0; g < sch.Q; g++) {
