@@ -201,6 +201,30 @@ def test_lammps_pair_styles_through_the_shim_driver(kind, prefix, name, ni_pot_f
             assert np.abs(out["vatom"] - ref["vatom"]).max() <= 1e-9
 
 
+@pytest.mark.parametrize("kind,prefix,name", [("plugin_annp_ni_b200", "annp_ni", "fcc3_perturbed"), ("plugin_anna_adp_b200", "anna_adp", "bcc4_perturbed")])
+def test_lammps_pair_styles_host_paths_of_the_other_two_styles(kind, prefix, name, ni_pot_file, anna_pot_file):
+    """Repeated calls on one list (page-locked arrays, types not re-sent), the pair-hybrid situation (forces staged and
+    added) and the device-neighbour mode for the Ni build of PairANNPB200 and for PairANNAADPB200.  The device-built list
+    holds the same atoms per row in index order instead of the golden's shuffled order: ANNA-ADP reproduces the forces to
+    rounding; the Ni copy's forces depend on the row order by construction (ni/src/pair_annp.cpp:734-735), so there only the
+    energies - which do not - are compared."""
+    from oracle import run_ref
+    if not run_ref.available(kind):
+        pytest.skip(f"{kind} not built")
+    cfg, elems, ref = util.load_case(name, prefix)
+    pot = ni_pot_file if prefix == "annp_ni" else anna_pot_file
+    one = run_ref.run_reference(kind, cfg, pot, elems, eflag=3, vflag=1 + 4)
+    many = run_ref.run_reference(kind, cfg, pot, elems, eflag=3, vflag=1 + 4, ncalls=3)
+    assert np.array_equal(many["f"], one["f"]) and np.array_equal(many["eatom"], one["eatom"])
+    hyb = run_ref.run_reference(kind, cfg, pot, elems, eflag=3, vflag=1 + 4, ncalls=2, env_extra={"ANNP_DRIVER_HYBRID": "1"})
+    assert np.array_equal(hyb["f"], one["f"]) and hyb["eng_vdwl"] == one["eng_vdwl"]
+    dev = run_ref.run_reference(kind, cfg, pot, elems, eflag=3, vflag=1 + 4, ncalls=2, env_extra={"ANNP_B200_NEIGH": "device"})
+    assert np.abs(dev["eatom"] - ref["eatom"]).max() <= 1e-9
+    if prefix != "annp_ni":
+        assert np.abs(dev["f"] - ref["f"]).max() <= 1e-9
+        assert np.abs(dev["virial"] - ref["virial_pair"]).max() <= 1e-8
+
+
 def test_ni_device_md_uses_the_descriptor_cutoff_for_its_list(ni_pot_file):
     """The Ni file's `Cut` (6.5 A) only sizes LAMMPS' list; nothing beyond Rc = 7.3699 Bohr = 3.9 A contributes.  The
     device-resident driver builds its list with the tighter radius: same forces to rounding (the surviving row entries
