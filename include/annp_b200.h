@@ -330,6 +330,22 @@ int annp_b200_set_halo_peers(annp_b200_handle h, int nranks, const int *send_cou
  * Plain stream work, no host synchronisation: a whole MD step may be captured in a CUDA graph. */
 int annp_b200_halo_forward(annp_b200_handle h, double *d_x, void *stream);
 int annp_b200_halo_reverse(annp_b200_handle h, double *d_f, void *stream);
+/* Peer scatter: the reverse halo FUSED into the force kernel (ranks of one node, fixed-point scatter mode).  Every rank
+ * exports its force accumulators (peer_export: cudaIpc handle, 64 bytes), the caller gathers the handles of all ranks and
+ * hands them to peer_open together with, for every ghost atom g of this rank, the rank that owns it (d_ghost_rank[g]) and
+ * the owner's local index (d_ghost_index[g] = the owner's send_index entry; device arrays that stay alive until the next
+ * peer_open).  From then on the force kernel adds the force on a ghost straight into its OWNER's accumulator with
+ * system-scope 64-bit integer atomics over NVLink, annp_b200_halo_reverse becomes a no-op and annp_b200_compute_device
+ * places one barrier (a one-element all-reduce on the handle's communicator) between the kernels and the conversion of the
+ * accumulators.  Integer addition commutes: forces are bit-identical to the exchange path.  Call both after
+ * annp_b200_set_halo_peers at every re-neighbouring (nall = nlocal + ghosts; the export re-allocates the accumulators if
+ * they must grow); annp_b200_halo_forward must precede every annp_b200_compute_device (it clears the accumulators before
+ * the peers can reach them). */
+int annp_b200_peer_export(annp_b200_handle h, int nall, char *ipc64);
+int annp_b200_peer_open(annp_b200_handle h, int nranks, const char *ipc64_all, int nghost, const int *d_ghost_rank,
+                        const int *d_ghost_index, void *stream);
+int annp_b200_peer_close(annp_b200_handle h);
+
 /* sum of d_buf[0..n) over the ranks of the communicator, in place (thermo scalars, the 12 Nose-Hoover tensors) */
 int annp_b200_allreduce_sum(annp_b200_handle h, double *d_buf, int n, void *stream);
 

@@ -139,6 +139,9 @@ PROTOTYPES = {
     "annp_b200_halo_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_halo_reverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_allreduce_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "annp_b200_peer_export": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p]),
+    "annp_b200_peer_open": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "annp_b200_peer_close": (C.c_int, [C.c_void_p]),
     "annp_b200_set_halo": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_halo_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "annp_b200_halo_unpack_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

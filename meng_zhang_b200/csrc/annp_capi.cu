@@ -38,6 +38,7 @@ void aux_halo_unpack_add(int nlocal, const long long *goff, const int *glist, co
 void aux_nve_initial(int n, double dt, double dtfm, double *x, double *v, const double *f, cudaStream_t s);
 void aux_max_disp2(int n, const double *x, const double *xref, double *out, cudaStream_t s);
 void aux_iota(int *p, int n, cudaStream_t s);
+extern "C" int annp_peer_barrier(annp_b200_handle h, cudaStream_t s);
 void aux_nve_final(int n, double dtfm, double *v, const double *f, cudaStream_t s);
 int aux_ke_blocks(int n);
 void aux_kinetic(int n, const double *v, double half_mass, double *partial, double *out, cudaStream_t s);
@@ -203,7 +204,8 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
   a.nbr = h->d_nbr.as<int>();
   a.fpair = fixed ? nullptr : h->d_fpair.as<double4>();
   a.facc = fixed ? h->d_facc.as<long long>() : nullptr;
-  if (fixed) CK(cudaMemsetAsync(h->d_facc.p, 0, sizeof(long long) * 3 * (size_t) std::max(nall, 1), s));
+  if (fixed && !(h->peer_on && h->peer_zeroed)) CK(cudaMemsetAsync(h->d_facc.p, 0, sizeof(long long) * 3 * (size_t) std::max(nall, 1), s));
+  h->peer_zeroed = false;
   a.fself = h->d_fself.as<double4>();
   a.vir_c = (want_vir || want_vatom) ? h->d_vir_c.as<double>() : nullptr;
   a.vpair = want_vatom ? h->d_vpair.as<double>() : nullptr;
@@ -213,6 +215,12 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
   a.inum = inum;
   a.capacity = h->capacity;
   for (int k = 0; k < 17; k++) a.gp[k] = h->hp.gparams[k];
+  // peer scatter: ghosts' forces go to their owners' accumulators (this rank's were zeroed before its forward exchange)
+  const bool peer = h->peer_on && fixed && nghost == h->g_nghost_recv;
+  a.peer_facc = peer ? h->d_peer_table.as<long long *>() : nullptr;
+  a.ghost_rank = peer ? h->peer_ghost_rank : nullptr;
+  a.ghost_index = peer ? h->peer_ghost_index : nullptr;
+  a.peer_nlocal = nlocal;
   a.work_list = nullptr;
   a.work_count = nullptr;
   a.work_ctr = &a.cnt->work;
@@ -244,6 +252,7 @@ int step_device(annp_b200_handle h, int nlocal, int nghost, const double *d_x, c
       h->launches += 1;
     }
   }
+  if (peer) { int rc = annp_peer_barrier(h, s); if (rc) return rc; }      // every rank's kernel has added its ghost forces
   if (d_f && fixed) {
     aux_finish_force(h->d_facc.as<long long>(), h->d_fself.as<double4>(), h->d_centre_of.as<int>(), d_f, nall, s);
     h->launches += 1;
@@ -530,8 +539,9 @@ void annp_b200_clear(annp_b200_handle h) {
                     &h->d_vpair, &h->d_partial, &h->d_counters, &h->d_engvir, &h->d_Gdbg, &h->d_dEdbg, &h->d_x, &h->d_type, &h->d_f,
                     &h->d_eatom, &h->d_vatom, &h->d_goff, &h->d_glist, &h->d_ke_partial};
   for (DevBuf *b : bufs) b->release();
+  annp_b200_peer_close(h);
   annp_b200_comm_destroy(h);
-  DevBuf *more[] = {&h->d_ovf_list, &h->d_sl_tile_cnt, &h->d_sl_tile_off, &h->d_sl_tile_sum, &h->d_sendbuf, &h->d_recvbuf};
+  DevBuf *more[] = {&h->d_ovf_list, &h->d_sl_tile_cnt, &h->d_sl_tile_off, &h->d_sl_tile_sum, &h->d_sendbuf, &h->d_recvbuf, &h->d_peer_table, &h->d_peer_sync};
   for (DevBuf *b : more) b->release();
   if (h->pin_list) cudaFreeHost(h->pin_list);
   for (int k = 0; k < annp_b200_handle_s::kEvRing; k++) {

@@ -86,6 +86,14 @@ struct ForceArgs {
   // ANNA-ADP: the 17 global ADP parameters ride in the kernel's parameter block (constant bank), so the tail reads them
   // as instruction operands instead of holding 34 registers
   double gp[17];
+  // Peer scatter (multi-GPU, annp_b200_peer_*): the force on a GHOST neighbour is added straight to the accumulator of
+  // its OWNER rank over NVLink instead of to this rank's ghost row - the reverse halo exchange fused into the force kernel.
+  //   peer_facc[r]  base of rank r's facc (IPC-mapped; entry of this rank = its own facc), null = feature off
+  //   ghost_rank / ghost_index [nghost]  owner rank and the owner's local index of ghost atom nlocal + g
+  long long *const *peer_facc;
+  const int *ghost_rank;
+  const int *ghost_index;
+  int peer_nlocal;
 };
 
 // number of work items of this launch and the centre index of item `item`
@@ -199,14 +207,26 @@ __device__ __forceinline__ void annp_mlp_forward_warp(const DevParams &P, const 
 }
 
 // add (fx, fy, fz) to the fixed-point accumulator of atom j; false if a component is outside the representable range
-__device__ __forceinline__ bool annp_fix_add(long long *facc, int j, double fx, double fy, double fz) {
+// (integer addition is associative and commutative, so the sum does not depend on which GPU adds first: the owner's
+// accumulator ends up with the same integer whether a ghost contribution arrives by peer atomic or by reverse exchange)
+__device__ __forceinline__ bool annp_fix_add(const ForceArgs &a, int j, double fx, double fy, double fz) {
   const double lim = (double) (1LL << ANNP_FIX_LIMIT_BITS), sc = (double) (1LL << ANNP_FIX_BITS);
   const bool ok = fabs(fx) < lim && fabs(fy) < lim && fabs(fz) < lim;      // false for NaN as well
   if (ok) {
-    unsigned long long *t = reinterpret_cast<unsigned long long *>(facc + 3 * (size_t) j);
-    atomicAdd(t, (unsigned long long) __double2ll_rn(fx * sc));
-    atomicAdd(t + 1, (unsigned long long) __double2ll_rn(fy * sc));
-    atomicAdd(t + 2, (unsigned long long) __double2ll_rn(fz * sc));
+    const unsigned long long ix = (unsigned long long) __double2ll_rn(fx * sc), iy = (unsigned long long) __double2ll_rn(fy * sc),
+                             iz = (unsigned long long) __double2ll_rn(fz * sc);
+    if (a.peer_facc && j >= a.peer_nlocal) {      // ghost: its owner's accumulator, system-scope atomics over NVLink
+      const int g = j - a.peer_nlocal;
+      unsigned long long *t = reinterpret_cast<unsigned long long *>(a.peer_facc[a.ghost_rank[g]] + 3 * (size_t) a.ghost_index[g]);
+      atomicAdd_system(t, ix);
+      atomicAdd_system(t + 1, iy);
+      atomicAdd_system(t + 2, iz);
+    } else {
+      unsigned long long *t = reinterpret_cast<unsigned long long *>(a.facc + 3 * (size_t) j);
+      atomicAdd(t, ix);
+      atomicAdd(t + 1, iy);
+      atomicAdd(t + 2, iz);
+    }
   }
   return ok;
 }

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kWarps * 32) annp_bp_force_kernel(const ForceA
       const double Fx = -gx, Fy = -gy, Fz = -gz;       // Fj of the reference before CFFORCE
       const int q = spos[s];
       if (a.facc) {     // fixed-point scatter (annp_device.cuh); else the per-entry buffer of the ordered gather
-        if (!annp_fix_add(a.facc, a.nbr[p0 + q] & ANNP_NEIGHMASK, Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE)) atomicExch(&a.cnt->bad_force, 1);
+        if (!annp_fix_add(a, a.nbr[p0 + q] & ANNP_NEIGHMASK, Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE)) atomicExch(&a.cnt->bad_force, 1);
       } else {
         a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
       }
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) annp_bp_fast_kernel(const Forc
       const double Fx = -gx, Fy = -gy, Fz = -gz;       // Fj of the reference before CFFORCE (:180-190)
       const int q = spos[s];
       if (a.facc) {     // fixed-point scatter (annp_device.cuh); else the per-entry buffer of the ordered gather
-        if (!annp_fix_add(a.facc, a.nbr[p0 + q] & ANNP_NEIGHMASK, Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE)) atomicExch(&a.cnt->bad_force, 1);
+        if (!annp_fix_add(a, a.nbr[p0 + q] & ANNP_NEIGHMASK, Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE)) atomicExch(&a.cnt->bad_force, 1);
       } else {
         a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
       }
@@ -940,7 +940,7 @@ __global__ void __launch_bounds__(kWarps * 32, ANNP_BP_PAIR_MINBLOCKS) annp_bp_p
       const double Fx = -gx, Fy = -gy, Fz = -gz;        // Fj of the reference before CFFORCE (:180-190)
       const int q = spos[lane];
       if (a.facc) {     // fixed-point scatter (annp_device.cuh); else the per-entry buffer of the ordered gather
-        if (!annp_fix_add(a.facc, a.nbr[p0 + q] & ANNP_NEIGHMASK, Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE)) atomicExch(&a.cnt->bad_force, 1);
+        if (!annp_fix_add(a, a.nbr[p0 + q] & ANNP_NEIGHMASK, Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE)) atomicExch(&a.cnt->bad_force, 1);
       } else {
         a.fpair[p0 + q] = make_double4(Fx * CFFORCE, Fy * CFFORCE, Fz * CFFORCE, 0.0);
       }

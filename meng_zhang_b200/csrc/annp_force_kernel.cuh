@@ -264,7 +264,7 @@ __device__ __forceinline__ void anna_adp_tail(const ForceArgs &a, const DevParam
       fz = df1 * B.x + aw * (y * lyz + z * lzz + x * lxz) + mz * au + z * df3;
     }
     if constexpr (FIXED) {                                            // f[j] += (fx, fy, fz), f[i] -=
-      if (!annp_fix_add(a.facc, a.nbr[p0 + q] & ANNP_NEIGHMASK, fx, fy, fz)) atomicExch(&a.cnt->bad_force, 1);
+      if (!annp_fix_add(a, a.nbr[p0 + q] & ANNP_NEIGHMASK, fx, fy, fz)) atomicExch(&a.cnt->bad_force, 1);
     } else {
       a.fpair[p0 + q] = make_double4(fx, fy, fz, 0.0);
     }
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(kWarps * 32, annp_min_blocks(NTSF)) annp_force
       const double Fx = mes * gx, Fy = mes * gy, Fz = mes * gz;     // pair_annp.cpp:197
       const int q = spos[s];
       if constexpr (FIXED) {
-        if (!annp_fix_add(a.facc, sj[s], Fx, Fy, Fz)) atomicExch(&a.cnt->bad_force, 1);
+        if (!annp_fix_add(a, sj[s], Fx, Fy, Fz)) atomicExch(&a.cnt->bad_force, 1);
       } else {
         a.fpair[p0 + q] = make_double4(Fx, Fy, Fz, 0.0);
       }

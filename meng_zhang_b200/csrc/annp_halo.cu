@@ -311,6 +311,7 @@ int annp_b200_set_halo_peers(annp_b200_handle h, int nranks, const int *send_cou
   if (ns != h->g_nghost) return fail(h, ANNP_B200_ESTATE, "set_halo_peers: send counts do not add up to the send list of annp_b200_set_halo");
   h->peer_send.assign(send_counts, send_counts + nranks);
   h->peer_recv.assign(recv_counts, recv_counts + nranks);
+  h->g_nghost_recv = (int) nr;
   CK(cudaSetDevice(h->device));
   CK(h->d_sendbuf.reserve(sizeof(double) * 3 * (size_t) std::max<long long>(ns, 1)));
   CK(h->d_recvbuf.reserve(sizeof(double) * 3 * (size_t) std::max<long long>(ns, 1)));
@@ -321,6 +322,12 @@ int annp_b200_set_halo_peers(annp_b200_handle h, int nranks, const int *send_cou
 int annp_b200_halo_forward(annp_b200_handle h, double *d_x, void *stream) {
   if (!h || !d_x) return ANNP_B200_EINVAL;
   cudaStream_t s = (cudaStream_t) stream;
+  if (h->peer_on) {
+    // peer scatter: this rank's accumulators must be clear before any peer's force kernel of this step can run, and a
+    // peer's kernel runs only after it has received this rank's positions from the exchange below
+    CK(cudaMemsetAsync(h->d_facc.p, 0, sizeof(long long) * 3 * (size_t) std::max(h->g_nlocal + h->g_nghost_recv, 1), s));
+    h->peer_zeroed = true;
+  }
   double *ghost = d_x + 3 * (size_t) h->g_nlocal;
   if (h->comm_size == 1) {                          // the receiver is this rank's own ghost block
     if (h->g_nghost > 0) { aux_halo_pack(h->g_nghost, h->g_owner, h->g_shift, d_x, ghost, s); h->launches += 1; }
@@ -335,6 +342,7 @@ int annp_b200_halo_forward(annp_b200_handle h, double *d_x, void *stream) {
 
 int annp_b200_halo_reverse(annp_b200_handle h, double *d_f, void *stream) {
   if (!h || !d_f) return ANNP_B200_EINVAL;
+  if (h->peer_on && h->scatter_fixed) return ANNP_B200_OK;      // peer scatter: the owners already hold the ghost contributions
   cudaStream_t s = (cudaStream_t) stream;
   if (h->comm_size > 1 && (int) h->peer_send.size() != h->comm_size) return fail(h, ANNP_B200_ESTATE, "halo_reverse before set_halo_peers");
   if (h->g_nghost == 0 && std::all_of(h->peer_recv.begin(), h->peer_recv.end(), [](int c) { return c == 0; })) return ANNP_B200_OK;
@@ -347,6 +355,78 @@ int annp_b200_halo_reverse(annp_b200_handle h, double *d_f, void *stream) {
   }
   aux_halo_unpack_add(h->g_nlocal, h->d_goff.as<long long>(), h->d_glist.as<int>(), src, d_f, s);
   h->launches += 1;
+  return ANNP_B200_OK;
+}
+
+// ---- peer scatter: the reverse halo fused into the force kernel -------------------------------------------------------
+// Every rank exports its fixed-point accumulator array (cudaIpc), maps the others' and tells the force kernel, for every ghost,
+// which rank owns it and under which local index.  The kernel then adds the force on a ghost straight into the owner's
+// accumulator with system-scope 64-bit integer atomics over NVLink; the per-step reverse exchange (grouped send/recv of the
+// ghost forces + ordered add) is replaced by one barrier (a one-element all-reduce) between the kernels and the conversion
+// of the accumulators.  Integer addition commutes, so the result is bit-identical to the exchange path and reproducible.
+// Ordering: a rank zeroes its accumulators BEFORE its forward exchange; a peer's kernel starts after that peer received this
+// rank's positions, i.e. after the zeroing; the barrier orders every peer's kernel before this rank reads its accumulators.
+int annp_b200_peer_export(annp_b200_handle h, int nall, char *ipc64) {
+  if (!h || !ipc64 || nall < 0) return ANNP_B200_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CK(cudaSetDevice(h->device));
+  CK(h->d_facc.reserve(sizeof(long long) * 3 * (size_t) std::max(nall, 1)));
+  cudaIpcMemHandle_t mh;
+  CK(cudaIpcGetMemHandle(&mh, h->d_facc.p));
+  memcpy(ipc64, &mh, 64);
+  return ANNP_B200_OK;
+}
+
+int annp_b200_peer_close(annp_b200_handle h) {
+  if (!h) return ANNP_B200_EINVAL;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void *&p : h->peer_ptr)
+    if (p) { cudaIpcCloseMemHandle(p); p = nullptr; }
+  h->peer_ptr.clear();
+  h->peer_key.clear();
+  h->peer_on = false;
+  return ANNP_B200_OK;
+}
+
+int annp_b200_peer_open(annp_b200_handle h, int nranks, const char *ipc64_all, int nghost, const int *d_ghost_rank,
+                        const int *d_ghost_index, void *stream) {
+  if (!h || !ipc64_all || nghost < 0 || (nghost > 0 && (!d_ghost_rank || !d_ghost_index))) return ANNP_B200_EINVAL;
+  if (nranks != h->comm_size) return fail(h, ANNP_B200_ESTATE, "peer_open: rank count differs from annp_b200_comm_init");
+  if (nranks > 1 && !h->nccl_comm) return fail(h, ANNP_B200_ESTATE, "peer scatter needs annp_b200_comm_init (step barrier)");
+  CK(cudaSetDevice(h->device));
+  h->peer_ptr.resize((size_t) nranks, nullptr);
+  h->peer_key.resize((size_t) nranks);
+  std::vector<long long *> table((size_t) nranks, nullptr);
+  for (int r = 0; r < nranks; r++) {
+    if (r == h->comm_rank) { table[r] = h->d_facc.as<long long>(); continue; }
+    const std::string key(ipc64_all + 64 * (size_t) r, 64);
+    if (!h->peer_ptr[r] || h->peer_key[r] != key) {        // the peer re-allocated its array (or first use): (re)map it
+      if (h->peer_ptr[r]) { CK(cudaDeviceSynchronize()); CK(cudaIpcCloseMemHandle(h->peer_ptr[r])); h->peer_ptr[r] = nullptr; }
+      cudaIpcMemHandle_t mh;
+      memcpy(&mh, key.data(), 64);
+      void *p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_ptr[r] = p;
+      h->peer_key[r] = key;
+    }
+    table[r] = (long long *) h->peer_ptr[r];
+  }
+  CK(h->d_peer_table.reserve(sizeof(long long *) * (size_t) nranks));
+  CK(h->d_peer_sync.reserve(sizeof(double)));
+  cudaStream_t s = (cudaStream_t) stream;
+  CK(cudaMemcpyAsync(h->d_peer_table.p, table.data(), sizeof(long long *) * (size_t) nranks, cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(h->d_peer_sync.p, 0, sizeof(double), s));
+  CK(cudaStreamSynchronize(s));          // `table` is a host temporary
+  h->peer_ghost_rank = d_ghost_rank;
+  h->peer_ghost_index = d_ghost_index;
+  h->peer_on = nranks > 1;
+  return ANNP_B200_OK;
+}
+
+// the barrier of the peer-scatter step: every rank's force kernel has finished adding (called by the per-step sequence)
+int annp_peer_barrier(annp_b200_handle h, cudaStream_t s) {
+  NK(nccl().AllReduce(h->d_peer_sync.p, h->d_peer_sync.p, 1, kNcclFloat64, kNcclSum, (ncclComm_t) h->nccl_comm, s));
   return ANNP_B200_OK;
 }
 

@@ -65,6 +65,14 @@ struct annp_b200_handle_s {
   int comm_rank = 0, comm_size = 1;
   std::vector<int> peer_send, peer_recv;   // atoms sent to / received from every rank per exchange
   DevBuf d_sendbuf, d_recvbuf;
+  // peer scatter (annp_halo.cu: annp_b200_peer_*): ghost contributions go straight to the owner rank's facc over NVLink
+  bool peer_on = false;
+  std::vector<void *> peer_ptr;            // IPC mappings of the other ranks' facc (null for this rank)
+  std::vector<std::string> peer_key;       // the 64 handle bytes each mapping was opened from
+  DevBuf d_peer_table, d_peer_sync;        // device array of the nranks base pointers; one double for the step barrier
+  const int *peer_ghost_rank = nullptr, *peer_ghost_index = nullptr;
+  bool peer_zeroed = false;                // the accumulators were zeroed by annp_b200_halo_forward of this step already
+  int g_nghost_recv = 0;                   // ghosts this rank holds (sum of the receive counts of set_halo_peers)
   int capacity = 0;
   bool need_calibrate = true;
   bool types_valid = false;           // host mode: d_type holds the types of the current atoms (annp_b200_compute with type == NULL)

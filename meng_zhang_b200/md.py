@@ -176,6 +176,11 @@ class DomainMD:
         if frozen_local is not None and np.any(frozen_local):
             self.frozen_idx = torch.as_tensor(np.nonzero(np.asarray(frozen_local))[0], dtype=torch.int64, device=self.dev)
         self.disp2 = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        # peer scatter (annp_b200_peer_*): ghost forces go straight to their owners' accumulators over NVLink, fusing the
+        # reverse exchange into the force kernel.  On by default with several ranks (ANNP_B200_PEER=0 keeps the NCCL
+        # reverse exchange); switched off for the run if any rank cannot map its peers' memory.
+        import os
+        self.peer = self.world > 1 and os.environ.get("ANNP_B200_PEER", "1") != "0"
         self._init_comm()
 
     def close(self):
@@ -183,6 +188,36 @@ class DomainMD:
         it) and wait for the device: call before pair.clear() when capture_step was used."""
         self._graph = None
         torch.cuda.synchronize(self.dev)
+
+    def _open_peers(self, nall):
+        """Peer scatter set-up of a re-neighbouring: exchange the IPC handles of the accumulator arrays and tell every ghost
+        its owner (rank, local index = the owner's send-list entry)."""
+        import sys
+        import torch.distributed as dist
+        # mappings of the previous list are dropped on every rank BEFORE any rank may re-allocate its (exported) array
+        self.L.annp_b200_peer_close(self.h)
+        dist.barrier(group=self.group)
+        buf = C.create_string_buffer(64)
+        rc = self.L.annp_b200_peer_export(self.h, nall, buf)
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(self.dev)
+        handles = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(handles, mine, group=self.group)
+        all64 = b"".join(bytes(t.cpu().numpy().tobytes()) for t in handles)
+        self._peer_gidx = torch.empty(max(self.nghost, 1), dtype=torch.int32, device=self.dev)[: self.nghost]
+        dist.all_to_all_single(self._peer_gidx, self.send_index.contiguous(), self.recv_counts, self.send_counts, group=self.group)
+        self._peer_grank = torch.repeat_interleave(torch.arange(self.world, dtype=torch.int32, device=self.dev),
+                                                   torch.as_tensor(self.recv_counts, device=self.dev)).contiguous()
+        if rc == 0:
+            rc = self.L.annp_b200_peer_open(self.h, self.world, all64, self.nghost, C.c_void_p(self._peer_grank.data_ptr()),
+                                            C.c_void_p(self._peer_gidx.data_ptr()), self._stream())
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok) == 0:            # some rank cannot map peer memory (no IPC in this container, ...): everybody falls back
+            if rc != 0:
+                print(f"annp_b200: peer scatter unavailable on rank {self.rank} ({self.L.annp_b200_last_error(self.h).decode()}); "
+                      "using the NCCL reverse exchange", file=sys.stderr)
+            self.L.annp_b200_peer_close(self.h)
+            self.peer = False
 
     def _init_comm(self):
         """NCCL communicator of the handle (annp_b200_comm_init): rank 0 draws the unique id, torch.distributed only carries
@@ -352,6 +387,8 @@ class DomainMD:
                                            C.c_void_p(self.send_shift.data_ptr()), self._stream()))
         sc_h, rc_h = np.array(self.send_counts, dtype=np.int32), np.array(self.recv_counts, dtype=np.int32)
         self._ck(self.L.annp_b200_set_halo_peers(self.h, self.world, sc_h.ctypes.data_as(capi.c_int_p), rc_h.ctypes.data_as(capi.c_int_p)))
+        if self.peer:
+            self._open_peers(nall)
         # ghost types travel once per re-neighbouring
         tl = self._type_local
         if self.world > 1:
