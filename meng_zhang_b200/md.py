@@ -177,10 +177,11 @@ class DomainMD:
             self.frozen_idx = torch.as_tensor(np.nonzero(np.asarray(frozen_local))[0], dtype=torch.int64, device=self.dev)
         self.disp2 = torch.zeros(1, dtype=torch.float64, device=self.dev)
         # peer scatter (annp_b200_peer_*): ghost forces go straight to their owners' accumulators over NVLink, fusing the
-        # reverse exchange into the force kernel.  On by default with several ranks (ANNP_B200_PEER=0 keeps the NCCL
-        # reverse exchange); switched off for the run if any rank cannot map its peers' memory.
+        # reverse exchange into the force kernel.  Bit-identical to the exchange path, but MEASURED SLOWER at the bench size
+        # (8 GPUs: 24.69 vs 24.33 ms per step - 22 M remote atomics per step lose against one 3.5 MB bulk transfer), so it
+        # is opt-in: ANNP_B200_PEER=1.  Switched off for the run if any rank cannot map its peers' memory.
         import os
-        self.peer = self.world > 1 and os.environ.get("ANNP_B200_PEER", "1") != "0"
+        self.peer = self.world > 1 and os.environ.get("ANNP_B200_PEER", "0") == "1"
         self._init_comm()
 
     def close(self):
