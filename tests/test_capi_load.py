@@ -85,3 +85,25 @@ def test_lammps_pair_style_binary_fails_loudly_without_gpu(built, fe_pot_file):
     cfg, elems, _ = util.load_case("cluster_ragged")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         run_ref.run_reference("plugin_annp_b200", cfg, fe_pot_file, elems)
+
+
+def test_header_is_plain_c_and_links(built, tmp_path):
+    """include/annp_b200.h is the drop-in boundary: it must compile as C11 (-pedantic) without any C++ / CUDA / torch type,
+    and a C program must link against the library with nothing but the header."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc unavailable")
+    src = tmp_path / "cabi.c"
+    src.write_text('#include "annp_b200.h"\n'
+                   'int main(void) {\n'
+                   '  annp_b200_stats st; annp_b200_params p; anna_b200_params q; (void) st; (void) p; (void) q;\n'
+                   '  return annp_b200_abi_version() == ANNP_B200_ABI_VERSION && annp_b200_device_count() >= 0 ? 0 : 1;\n'
+                   '}\n')
+    exe = tmp_path / "cabi"
+    libdir = os.path.dirname(capi.LIB_PATH)
+    p = subprocess.run([gcc, "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-L", libdir, "-lannp_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
